@@ -1,0 +1,371 @@
+// Device half of the C-ABI: context (pinned staging / pinned row-group cache / host copy threads), upload, decode,
+// and the thin extern "C" wrappers around the post-processing kernels.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <stdexcept>
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/pst_b200.h"
+#include "host_state.h"
+#include "kernels.h"
+
+using namespace pst;
+
+namespace {
+
+struct CudaFail : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+inline void ck(cudaError_t e, const char *what) {
+    if (e != cudaSuccess) throw CudaFail(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+// Minimal fork-join pool for the host-side staging copies (mmap -> pinned).
+class CopyPool {
+public:
+    explicit CopyPool(int n) {
+        for (int i = 0; i < n; i++) workers_.emplace_back([this] { run(); });
+    }
+    ~CopyPool() {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : workers_) t.join();
+    }
+    int size() const { return (int)workers_.size(); }
+    // runs fn(i) for i in [0, n) on the pool and the calling thread; returns when all are done
+    void parallel_for(int n, const std::function<void(int)> &fn) {
+        if (n <= 0) return;
+        if (workers_.empty() || n == 1) {
+            for (int i = 0; i < n; i++) fn(i);
+            return;
+        }
+        std::unique_lock<std::mutex> g(m_);
+        fn_ = &fn;
+        next_ = 0;
+        total_ = n;
+        pending_ = n;
+        gen_++;
+        g.unlock();
+        cv_.notify_all();
+        work();  // the caller helps
+        g.lock();
+        done_cv_.wait(g, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+private:
+    void work() {
+        for (;;) {
+            int i;
+            {
+                std::lock_guard<std::mutex> g(m_);
+                if (!fn_ || next_ >= total_) return;
+                i = next_++;
+            }
+            (*fn_)(i);
+            {
+                std::lock_guard<std::mutex> g(m_);
+                if (--pending_ == 0) done_cv_.notify_all();
+            }
+        }
+    }
+    void run() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [&] { return stop_ || gen_ != seen; });
+                if (stop_) return;
+                seen = gen_;
+            }
+            work();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(int)> *fn_ = nullptr;
+    int next_ = 0, total_ = 0, pending_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+
+struct PinnedBuf {
+    uint8_t *ptr = nullptr;
+    int64_t cap = 0;
+    cudaEvent_t ev = nullptr;  // last H2D that read from this buffer
+    bool busy = false;
+};
+
+}  // namespace
+
+struct pst_ctx {
+    int device = 0;
+    int64_t cache_budget = 0;
+    int64_t cache_bytes = 0;
+    std::unordered_map<uint64_t, PinnedBuf> cache;
+    PinnedBuf ring[3];
+    int ring_next = 0;
+    std::unique_ptr<CopyPool> pool;
+    std::mutex mu;
+    // counters
+    std::atomic<int64_t> bytes_staged{0}, bytes_h2d{0}, cache_hits{0}, cache_misses{0}, pages_decoded{0},
+        rowgroups_decoded{0}, kernels_launched{0};
+};
+
+#define PST_TRY try {
+#define PST_CATCH(ret)                \
+    }                                 \
+    catch (const std::exception &e) { \
+        pst::set_error(e.what());     \
+        return ret;                   \
+    }
+
+static void fill_parallel(pst_ctx *c, const pst_plan *p, uint8_t *dst) {
+    // split the pages into ~equal byte ranges, one task per range
+    int64_t npages = (int64_t)p->pages.size();
+    int tasks = c->pool ? c->pool->size() + 1 : 1;
+    if (p->payload_bytes < (4 << 20)) tasks = 1;
+    std::vector<int64_t> cuts(1, 0);
+    int64_t per = p->payload_bytes / tasks + 1, acc = 0;
+    for (int64_t i = 0; i < npages; i++) {
+        acc += p->pages[i].d.comp_size;
+        if (acc >= per && (int)cuts.size() < tasks) {
+            cuts.push_back(i + 1);
+            acc = 0;
+        }
+    }
+    if (cuts.back() != npages) cuts.push_back(npages);
+    int n = (int)cuts.size() - 1;
+    std::function<void(int)> fn = [&](int t) { pst_plan_fill_raw(p, dst, cuts[t], cuts[t + 1]); };
+    if (n <= 0) {
+        pst_plan_fill_raw(p, dst, 0, 0);
+        return;
+    }
+    if (c->pool) c->pool->parallel_for(n, fn);
+    else for (int t = 0; t < n; t++) fn(t);
+}
+
+extern "C" {
+
+int pst_has_cuda(void) { return 1; }
+
+int pst_ctx_create(int device, int64_t pinned_cache_bytes, int copy_threads, pst_ctx **out) {
+    PST_TRY
+    *out = nullptr;
+    ck(cudaSetDevice(device), "cudaSetDevice");
+    ck(cudaFree(0), "cuda context init");
+    ck(configure_decode_kernels(), "configure kernels");
+    std::unique_ptr<pst_ctx> c(new pst_ctx());
+    c->device = device;
+    c->cache_budget = pinned_cache_bytes;
+    if (copy_threads < 0) {
+        unsigned hc = std::thread::hardware_concurrency();
+        copy_threads = hc > 2 ? (int)std::min<unsigned>(hc - 1, 12) : 0;
+    }
+    if (copy_threads > 0) c->pool.reset(new CopyPool(copy_threads));
+    *out = c.release();
+    return 0;
+    PST_CATCH(1)
+}
+
+void pst_ctx_destroy(pst_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (auto &kv : c->cache)
+        if (kv.second.ptr) cudaFreeHost(kv.second.ptr);
+    for (auto &b : c->ring) {
+        if (b.ev) {
+            cudaEventSynchronize(b.ev);
+            cudaEventDestroy(b.ev);
+        }
+        if (b.ptr) cudaFreeHost(b.ptr);
+    }
+    delete c;
+}
+
+int pst_ctx_stats_json(pst_ctx *c, char *buf, size_t cap) {
+    int n = snprintf(buf, cap,
+                     "{\"bytes_staged\":%lld,\"bytes_h2d\":%lld,\"pinned_cache_bytes\":%lld,\"pinned_cache_hits\":%lld,"
+                     "\"pinned_cache_misses\":%lld,\"pages_decoded\":%lld,\"rowgroups_decoded\":%lld,"
+                     "\"kernels_launched\":%lld}",
+                     (long long)c->bytes_staged.load(), (long long)c->bytes_h2d.load(), (long long)c->cache_bytes,
+                     (long long)c->cache_hits.load(), (long long)c->cache_misses.load(),
+                     (long long)c->pages_decoded.load(), (long long)c->rowgroups_decoded.load(),
+                     (long long)c->kernels_launched.load());
+    return (n < 0 || (size_t)n >= cap) ? 1 : 0;
+}
+
+int pst_plan_upload(pst_ctx *c, pst_plan *p, uint64_t d_arena, uint64_t stream) {
+    PST_TRY
+    cudaStream_t s = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> g(c->mu);
+    ck(cudaSetDevice(c->device), "cudaSetDevice");
+    const int64_t need = p->raw_bytes;
+    uint8_t *src = nullptr;
+    auto it = c->cache.find(p->cache_key);
+    if (it != c->cache.end() && it->second.cap >= need) {
+        src = it->second.ptr;
+        c->cache_hits++;
+    } else {
+        c->cache_misses++;
+        bool cacheable = c->cache_bytes + need <= c->cache_budget;
+        PinnedBuf *slot;
+        if (cacheable) {
+            PinnedBuf nb;
+            ck(cudaHostAlloc((void **)&nb.ptr, (size_t)need, cudaHostAllocDefault), "cudaHostAlloc (pinned cache)");
+            nb.cap = need;
+            c->cache_bytes += need;
+            slot = &(c->cache[p->cache_key] = nb);
+        } else {
+            slot = &c->ring[c->ring_next];
+            c->ring_next = (c->ring_next + 1) % 3;
+            if (slot->ev) ck(cudaEventSynchronize(slot->ev), "staging ring wait");
+            if (slot->cap < need) {
+                if (slot->ptr) cudaFreeHost(slot->ptr);
+                slot->ptr = nullptr;
+                int64_t cap = need + need / 8;
+                ck(cudaHostAlloc((void **)&slot->ptr, (size_t)cap, cudaHostAllocDefault), "cudaHostAlloc (staging ring)");
+                slot->cap = cap;
+            }
+            if (!slot->ev) ck(cudaEventCreateWithFlags(&slot->ev, cudaEventDisableTiming), "cudaEventCreate");
+        }
+        fill_parallel(c, p, slot->ptr);
+        c->bytes_staged += p->payload_bytes;
+        src = slot->ptr;
+        if (!cacheable) {
+            ck(cudaMemcpyAsync((void *)d_arena, src, (size_t)need, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync H2D");
+            ck(cudaEventRecord(slot->ev, s), "cudaEventRecord");
+            c->bytes_h2d += need;
+            return 0;
+        }
+    }
+    ck(cudaMemcpyAsync((void *)d_arena, src, (size_t)need, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync H2D");
+    c->bytes_h2d += need;
+    return 0;
+    PST_CATCH(1)
+}
+
+int pst_plan_decode(pst_ctx *c, pst_plan *p, uint64_t d_arena, uint64_t d_out, uint64_t d_status, uint64_t stream,
+                    int *launches) {
+    PST_TRY
+    cudaStream_t s = (cudaStream_t)stream;
+    uint8_t *arena = (uint8_t *)d_arena;
+    uint8_t *outp = (uint8_t *)d_out;
+    int32_t *status = (int32_t *)d_status;
+    const DevCol *cols = (const DevCol *)(arena + p->cols_off);
+    const DevPage *pages = (const DevPage *)(arena + p->pages_off);
+    const int32_t *comp = (const int32_t *)(arena + p->comp_list_off);
+    const int32_t *data = (const int32_t *)(arena + p->data_list_off);
+    const int32_t *dict = (const int32_t *)(arena + p->dict_list_off);
+    int nl = 0;
+    if (!p->compressed_pages.empty()) {
+        ck(launch_snappy(arena, pages, comp, (int)p->compressed_pages.size(), status, s), "snappy launch");
+        nl++;
+    }
+    if (!p->ba_dict_pages.empty()) {
+        ck(launch_ba_dict_index(arena, pages, cols, dict, (int)p->ba_dict_pages.size(), status, s), "dict index launch");
+        nl++;
+    }
+    if (!p->data_pages.empty()) {
+        ck(launch_decode_pages(arena, outp, cols, pages, data, (int)p->data_pages.size(), status, s), "decode launch");
+        nl++;
+    }
+    if (launches) *launches = nl;
+    if (c) {
+        c->pages_decoded += (int64_t)p->pages.size();
+        c->rowgroups_decoded++;
+        c->kernels_launched += nl;
+    }
+    return 0;
+    PST_CATCH(1)
+}
+
+// ---- post-processing wrappers -------------------------------------------------------------------------------
+#define WRAP(expr, what)              \
+    PST_TRY                           \
+    ck((expr), what);                 \
+    return 0;                         \
+    PST_CATCH(1)
+
+int pst_nullable_to_f64(uint64_t values, uint64_t valid, int64_t n, int physical_type, int bit_width, int is_unsigned,
+                        uint64_t out, uint64_t stream) {
+    WRAP(launch_nullable_to_f64((const void *)values, (const uint8_t *)valid, n, physical_type, bit_width, is_unsigned,
+                                (double *)out, (cudaStream_t)stream), "nullable_to_f64")
+}
+int pst_narrow_int32(uint64_t src, int64_t n, int bit_width, uint64_t dst, uint64_t stream) {
+    WRAP(launch_narrow_int32((const int32_t *)src, n, bit_width, (void *)dst, (cudaStream_t)stream), "narrow_int32")
+}
+int pst_gather_rows(uint64_t src, uint64_t idx, int64_t n_out, int64_t row_bytes, uint64_t dst, uint64_t stream) {
+    WRAP(launch_gather_rows((const uint8_t *)src, (const int64_t *)idx, n_out, row_bytes, (uint8_t *)dst,
+                            (cudaStream_t)stream), "gather_rows")
+}
+int pst_npy_batch(uint64_t base, uint64_t offs, uint64_t lens, uint64_t row_idx, int64_t n, int64_t data_off,
+                  int64_t payload_bytes, uint64_t dst, uint64_t d_status, uint64_t stream) {
+    WRAP(launch_npy_batch((const uint8_t *)base, (const int64_t *)offs, (const int32_t *)lens, (const int64_t *)row_idx,
+                          n, data_off, payload_bytes, (uint8_t *)dst, (int32_t *)d_status, (cudaStream_t)stream),
+         "npy_batch")
+}
+int64_t pst_png_work_bytes(int height, int width, int channels, int sample_bytes) {
+    return png_work_bytes(height, width, channels, sample_bytes);
+}
+int pst_png_batch(uint64_t base, uint64_t offs, uint64_t lens, uint64_t row_idx, int64_t n, int height, int width,
+                  int channels, int sample_bytes, uint64_t dst, uint64_t d_work, uint64_t d_status, uint64_t stream) {
+    WRAP(launch_png_batch((const uint8_t *)base, (const int64_t *)offs, (const int32_t *)lens, (const int64_t *)row_idx,
+                          n, height, width, channels, sample_bytes, (uint8_t *)dst, (uint8_t *)d_work,
+                          (int32_t *)d_status, (cudaStream_t)stream), "png_batch")
+}
+int pst_mask_in_set_i64(uint64_t keys, int key_bytes, int key_unsigned, int64_t n, uint64_t set_sorted, int64_t set_n,
+                        uint64_t mask, uint64_t stream) {
+    WRAP(launch_mask_in_set((const void *)keys, key_bytes, key_unsigned, n, (const int64_t *)set_sorted, set_n,
+                            (uint8_t *)mask, (cudaStream_t)stream), "mask_in_set")
+}
+int pst_mask_md5_split_i64(uint64_t keys, int key_bytes, int key_unsigned, int64_t n, double lo, double hi,
+                           uint64_t mask, uint64_t stream) {
+    WRAP(launch_mask_md5_split((const void *)keys, key_bytes, key_unsigned, n, lo, hi, (uint8_t *)mask,
+                               (cudaStream_t)stream), "mask_md5_split")
+}
+int64_t pst_compact_tmp_bytes(int64_t n) { return compact_tmp_bytes(n); }
+int pst_mask_compact(uint64_t mask, int64_t n, uint64_t out_idx, uint64_t d_count, uint64_t d_tmp, uint64_t stream) {
+    WRAP(launch_mask_compact((const uint8_t *)mask, n, (int64_t *)out_idx, (int64_t *)d_count, (void *)d_tmp,
+                             (cudaStream_t)stream), "mask_compact")
+}
+int pst_normalize(uint64_t src, int src_dtype, int64_t n, float mean, float stddev, uint64_t dst, int dst_dtype,
+                  uint64_t stream) {
+    WRAP(launch_normalize((const void *)src, src_dtype, n, mean, stddev, (void *)dst, dst_dtype, (cudaStream_t)stream),
+         "normalize")
+}
+int pst_ngram_valid_starts(uint64_t ts, int64_t n, int length, int64_t delta, uint64_t ok, uint64_t d_status,
+                           uint64_t stream) {
+    WRAP(launch_ngram_valid_starts((const int64_t *)ts, n, length, delta, (uint8_t *)ok, (int32_t *)d_status,
+                                   (cudaStream_t)stream), "ngram_valid_starts")
+}
+int pst_ngram_gather(uint64_t src, uint64_t starts, int64_t n_windows, int length, int64_t row_bytes, uint64_t dst,
+                     uint64_t stream) {
+    WRAP(launch_ngram_gather((const uint8_t *)src, (const int64_t *)starts, n_windows, length, row_bytes,
+                             (uint8_t *)dst, (cudaStream_t)stream), "ngram_gather")
+}
+int pst_sanitize(uint64_t src, int64_t n, int kind, uint64_t dst, uint64_t stream) {
+    WRAP(launch_sanitize((const void *)src, n, kind, (void *)dst, (cudaStream_t)stream), "sanitize")
+}
+int pst_list_uniform(uint64_t rep, uint64_t def, int64_t n, int max_def, int64_t list_len, uint64_t d_flags,
+                     uint64_t stream) {
+    WRAP(launch_list_uniform((const uint8_t *)rep, (const uint8_t *)def, n, max_def, list_len, (int64_t *)d_flags,
+                             (cudaStream_t)stream), "list_uniform")
+}
+
+}  // extern "C"

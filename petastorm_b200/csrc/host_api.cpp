@@ -1,0 +1,536 @@
+// Host-only half of the C-ABI: file mapping, footer, row-group plan (page walk + HBM layout). No CUDA in here.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <memory>
+#include <cstring>
+#include <stdexcept>
+
+#include "../../include/pst_b200.h"
+#include "host_state.h"
+
+namespace pst {
+static thread_local std::string g_last_error;
+void set_error(const std::string &msg) { g_last_error = msg; }
+
+// --------------------------------------------------------------------------------------------------------------
+// Snappy "peek": decode only the first `want` bytes of a raw snappy block (format_description.txt of google/snappy).
+// Used by the planner to learn the byte length of the level sections of a compressed V1 data page so that the
+// value section can be placed 16-byte aligned in HBM.
+// --------------------------------------------------------------------------------------------------------------
+size_t snappy_peek(const uint8_t *src, size_t n, uint8_t *out, size_t want) {
+    size_t ip = 0;
+    // preamble: uncompressed length varint
+    uint64_t ulen = 0;
+    int shift = 0;
+    for (;;) {
+        if (ip >= n) return 0;
+        uint8_t b = src[ip++];
+        ulen |= (uint64_t)(b & 0x7f) << shift;
+        if (!(b & 0x80)) break;
+        shift += 7;
+        if (shift > 35) return 0;
+    }
+    if (want > ulen) want = (size_t)ulen;
+    size_t op = 0;
+    while (op < want && ip < n) {
+        uint8_t tag = src[ip++];
+        size_t len, offset = 0;
+        switch (tag & 3) {
+            case 0: {
+                len = (tag >> 2) + 1;
+                if (len > 60) {
+                    size_t nb = len - 60;
+                    if (ip + nb > n) return op;
+                    len = 0;
+                    for (size_t i = 0; i < nb; i++) len |= (size_t)src[ip + i] << (8 * i);
+                    len += 1;
+                    ip += nb;
+                }
+                size_t take = std::min(len, want - op);
+                if (ip + take > n) return op;
+                memcpy(out + op, src + ip, take);
+                op += take;
+                ip += len;
+                continue;
+            }
+            case 1:
+                if (ip >= n) return op;
+                len = ((tag >> 2) & 7) + 4;
+                offset = ((size_t)(tag >> 5) << 8) | src[ip++];
+                break;
+            case 2:
+                if (ip + 2 > n) return op;
+                len = (tag >> 2) + 1;
+                offset = src[ip] | ((size_t)src[ip + 1] << 8);
+                ip += 2;
+                break;
+            default:
+                if (ip + 4 > n) return op;
+                len = (tag >> 2) + 1;
+                offset = src[ip] | ((size_t)src[ip + 1] << 8) | ((size_t)src[ip + 2] << 16) | ((size_t)src[ip + 3] << 24);
+                ip += 4;
+                break;
+        }
+        if (offset == 0 || offset > op) return op;
+        for (size_t i = 0; i < len && op < want; i++, op++) out[op] = out[op - offset];
+    }
+    return op;
+}
+}  // namespace pst
+
+using namespace pst;
+
+#define PST_TRY try {
+#define PST_CATCH(ret)                      \
+    }                                       \
+    catch (const std::exception &e) {       \
+        pst::set_error(e.what());           \
+        return ret;                         \
+    }
+
+extern "C" {
+
+const char *pst_last_error(void) { return pst::g_last_error.c_str(); }
+int pst_abi_version(void) { return PST_ABI_VERSION; }
+
+int pst_file_open(const char *path, pst_file **out) {
+    PST_TRY
+    *out = nullptr;
+    int fd = ::open(path, O_RDONLY | O_CLOEXEC);
+    if (fd < 0) throw std::runtime_error(std::string("cannot open ") + path + ": " + strerror(errno));
+    struct stat st;
+    if (fstat(fd, &st) != 0) {
+        ::close(fd);
+        throw std::runtime_error(std::string("fstat failed for ") + path);
+    }
+    size_t size = (size_t)st.st_size;
+    if (size < 12) {
+        ::close(fd);
+        throw std::runtime_error(std::string(path) + " is too small to be a parquet file");
+    }
+    void *map = mmap(nullptr, size, PROT_READ, MAP_SHARED, fd, 0);
+    if (map == MAP_FAILED) {
+        ::close(fd);
+        throw std::runtime_error(std::string("mmap failed for ") + path + ": " + strerror(errno));
+    }
+    std::unique_ptr<pst_file> f(new pst_file());
+    f->path = path;
+    f->fd = fd;
+    f->map = static_cast<const uint8_t *>(map);
+    f->size = size;
+    f->mtime_ns = (int64_t)st.st_mtim.tv_sec * 1000000000ll + st.st_mtim.tv_nsec;
+    auto fail = [&](const std::string &m) {
+        munmap(map, size);
+        ::close(fd);
+        f->fd = -1;
+        throw std::runtime_error(std::string(path) + ": " + m);
+    };
+    if (memcmp(f->map + size - 4, "PAR1", 4) != 0 || memcmp(f->map, "PAR1", 4) != 0) {
+        if (memcmp(f->map + size - 4, "PARE", 4) == 0) fail("encrypted parquet footers are not supported");
+        fail("missing PAR1 magic");
+    }
+    uint32_t flen;
+    memcpy(&flen, f->map + size - 8, 4);
+    if ((size_t)flen + 12 > size) fail("footer length exceeds the file size");
+    try {
+        parse_file_meta(f->map + size - 8 - flen, flen, f->meta);
+    } catch (const std::exception &e) {
+        fail(std::string("footer parse failed: ") + e.what());
+    }
+    f->schema_json = schema_json(f->meta);
+    *out = f.release();
+    return 0;
+    PST_CATCH(1)
+}
+
+void pst_file_close(pst_file *f) {
+    if (!f) return;
+    if (f->map) munmap(const_cast<uint8_t *>(f->map), f->size);
+    if (f->fd >= 0) ::close(f->fd);
+    delete f;
+}
+
+int pst_file_num_row_groups(const pst_file *f) { return (int)f->meta.row_groups.size(); }
+int64_t pst_file_num_rows(const pst_file *f) { return f->meta.num_rows; }
+int64_t pst_file_row_group_num_rows(const pst_file *f, int rg) {
+    if (rg < 0 || rg >= (int)f->meta.row_groups.size()) return -1;
+    return f->meta.row_groups[rg].num_rows;
+}
+int pst_file_num_columns(const pst_file *f) { return (int)f->meta.leaves.size(); }
+
+int pst_file_schema_json(const pst_file *f, const char **json, size_t *len) {
+    *json = f->schema_json.c_str();
+    *len = f->schema_json.size();
+    return 0;
+}
+
+int pst_file_num_kv(const pst_file *f) { return (int)f->meta.kv.size(); }
+int pst_file_kv_at(const pst_file *f, int i, const char **key, size_t *klen, const uint8_t **val, size_t *vlen) {
+    if (i < 0 || i >= (int)f->meta.kv.size()) {
+        set_error("kv index out of range");
+        return 1;
+    }
+    *key = f->meta.kv[i].first.data();
+    *klen = f->meta.kv[i].first.size();
+    *val = reinterpret_cast<const uint8_t *>(f->meta.kv[i].second.data());
+    *vlen = f->meta.kv[i].second.size();
+    return 0;
+}
+int pst_file_kv_metadata(const pst_file *f, const char *key, const uint8_t **val, size_t *len) {
+    for (const auto &kv : f->meta.kv)
+        if (kv.first == key) {
+            *val = reinterpret_cast<const uint8_t *>(kv.second.data());
+            *len = kv.second.size();
+            return 0;
+        }
+    *val = nullptr;
+    *len = 0;
+    return 1;
+}
+
+int pst_file_chunk_info(const pst_file *f, int rg, int col, pst_chunk_info *out) {
+    if (rg < 0 || rg >= (int)f->meta.row_groups.size() || col < 0 || col >= (int)f->meta.leaves.size()) {
+        set_error("row group / column out of range");
+        return 1;
+    }
+    const ColumnChunkMeta &c = f->meta.row_groups[rg].columns[col];
+    out->physical_type = c.type;
+    out->codec = c.codec;
+    out->num_values = c.num_values;
+    out->data_page_offset = c.data_page_offset;
+    out->dictionary_page_offset = c.dictionary_page_offset > 0 ? c.dictionary_page_offset : -1;
+    out->total_compressed_size = c.total_compressed_size;
+    out->total_uncompressed_size = c.total_uncompressed_size;
+    out->start_offset = c.start_offset();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------------------------
+static int level_bits(int max_level) {
+    int b = 0;
+    while ((1 << b) <= max_level) b++;
+    return max_level == 0 ? 0 : b;
+}
+
+// Byte offset of the value section inside the uncompressed image of a V1 data page, or -1 if it cannot be learned
+// from the first bytes of the page.
+static int64_t v1_values_offset(const uint8_t *payload, size_t n, int codec, int max_rep, int max_def, int rep_enc,
+                                int def_enc, int num_values) {
+    if (max_rep == 0 && max_def == 0) return 0;
+    uint8_t head[512];
+    size_t have;
+    if (codec == PST_CODEC_NONE) {
+        have = std::min(n, sizeof head);
+        memcpy(head, payload, have);
+    } else if (codec == PST_CODEC_SNAPPY) {
+        have = snappy_peek(payload, n, head, sizeof head);
+    } else {
+        return -1;
+    }
+    size_t pos = 0;
+    auto section = [&](int max_level, int enc) -> bool {
+        if (max_level == 0) return true;
+        if (enc == ENC_RLE) {
+            if (pos + 4 > have) return false;
+            uint32_t len;
+            memcpy(&len, head + pos, 4);
+            pos += 4 + (size_t)len;
+            return true;
+        }
+        if (enc == ENC_BIT_PACKED) {
+            pos += ((size_t)num_values * level_bits(max_level) + 7) / 8;
+            return true;
+        }
+        return false;
+    };
+    if (!section(max_rep, rep_enc)) return -1;
+    if (pos > have && max_def > 0 && def_enc == ENC_RLE) return -1;  // cannot see the def length prefix
+    if (!section(max_def, def_enc)) return -1;
+    return (int64_t)pos;
+}
+
+int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_plan **out) {
+    PST_TRY
+    *out = nullptr;
+    if (rg < 0 || rg >= (int)f->meta.row_groups.size()) throw std::runtime_error("row group index out of range");
+    if (ncols <= 0) throw std::runtime_error("a plan needs at least one column");
+    const RowGroupMeta &g = f->meta.row_groups[rg];
+    std::unique_ptr<pst_plan> p(new pst_plan());
+    p->file = f;
+    p->rg = rg;
+    p->num_rows = g.num_rows;
+    p->cols.assign(cols, cols + ncols);
+    p->dcols.resize(ncols);
+
+    int64_t raw_cur = 0;      // cursor inside the raw region
+    int64_t scratch_cur = 0;  // cursor inside the scratch region (relative; rebased after raw size is known)
+    std::vector<int64_t> scratch_rel;  // per page: relative scratch offset or -1
+    std::vector<int64_t> dict_index_rel(ncols, -1);
+
+    for (int slot = 0; slot < ncols; slot++) {
+        int col = cols[slot];
+        if (col < 0 || col >= (int)f->meta.leaves.size()) throw std::runtime_error("column index out of range");
+        const ColumnChunkMeta &c = g.columns[col];
+        const LeafColumn &leaf = f->meta.leaves[col];
+        const SchemaElement &se = f->meta.schema[leaf.schema_index];
+        if (!c.file_path.empty()) throw std::runtime_error("column chunks stored in external files are not supported");
+        if (c.codec != PST_CODEC_NONE && c.codec != PST_CODEC_SNAPPY)
+            throw std::runtime_error("unsupported compression codec " + std::to_string(c.codec) +
+                                     " (supported: UNCOMPRESSED, SNAPPY) in column " + se.name);
+        DevCol &dc = p->dcols[slot];
+        memset(&dc, 0, sizeof dc);
+        dc.ptype = c.type;
+        switch (c.type) {
+            case PST_BOOLEAN: dc.width = 1; break;
+            case PST_INT32: case PST_FLOAT: dc.width = 4; break;
+            case PST_INT64: case PST_DOUBLE: dc.width = 8; break;
+            case PST_INT96: dc.width = 12; break;
+            case PST_FIXED_LEN_BYTE_ARRAY: dc.width = se.type_length; break;
+            case PST_BYTE_ARRAY: dc.width = 0; break;
+            default: throw std::runtime_error("unknown physical type");
+        }
+        dc.max_def = leaf.max_def;
+        dc.max_rep = leaf.max_rep;
+        dc.num_values = c.num_values;
+        dc.dict_img_off = -1;
+        dc.dict_page = -1;
+        dc.dict_index_off = -1;
+        dc.values_off = dc.valid_off = dc.rep_off = dc.def_off = dc.lens_off = -1;
+
+        int64_t off = c.start_offset();
+        int64_t chunk_end = off + c.total_compressed_size;
+        int64_t seen = 0;
+        int ordinal = 0;
+        while (seen < c.num_values) {
+            if (off < 0 || (size_t)off >= f->size || (c.total_compressed_size > 0 && off >= chunk_end))
+                throw std::runtime_error("column chunk of " + se.name + " ended before all values were found");
+            PageHeader h;
+            parse_page_header(f->map + off, std::min<size_t>(f->size - (size_t)off, 1 << 20), h);
+            int64_t payload = off + (int64_t)h.header_size;
+            if (h.compressed_page_size < 0 || (size_t)(payload + h.compressed_page_size) > f->size)
+                throw std::runtime_error("page payload exceeds the file size");
+            off = payload + h.compressed_page_size;
+            if (h.type == 1) continue;  // INDEX_PAGE
+            HostPage hp;
+            memset(&hp.d, 0, sizeof hp.d);
+            hp.file_off = payload;
+            DevPage &d = hp.d;
+            d.comp_size = h.compressed_page_size;
+            d.uncomp_size = h.uncompressed_page_size;
+            d.num_values = h.num_values;
+            d.col = (int16_t)slot;
+            d.encoding = (uint8_t)h.encoding;
+            d.codec = (uint8_t)c.codec;
+            d.page_ordinal = ordinal++;
+            d.def_bytes = d.rep_bytes = -1;
+            int64_t values_off_in_image = -1;
+            if (h.type == 2) {
+                d.kind = PK_DICT;
+                if (h.encoding != ENC_PLAIN && h.encoding != ENC_PLAIN_DICTIONARY)
+                    throw std::runtime_error("dictionary page with unsupported encoding");
+                if (dc.dict_page >= 0) throw std::runtime_error("more than one dictionary page in a column chunk");
+                dc.dict_page = (int32_t)p->pages.size();
+                dc.dict_count = h.num_values;
+                values_off_in_image = 0;
+            } else if (h.type == 0) {
+                d.kind = PK_DATA_V1;
+                d.def_enc = (uint8_t)h.def_encoding;
+                d.rep_enc = (uint8_t)h.rep_encoding;
+                d.first_value = (int32_t)seen;
+                seen += h.num_values;
+                values_off_in_image = v1_values_offset(f->map + payload, (size_t)h.compressed_page_size, c.codec,
+                                                       leaf.max_rep, leaf.max_def, h.rep_encoding, h.def_encoding,
+                                                       h.num_values);
+            } else if (h.type == 3) {
+                d.kind = PK_DATA_V2;
+                d.def_bytes = h.def_bytes;
+                d.rep_bytes = h.rep_bytes;
+                d.v2_compressed = h.is_compressed ? 1 : 0;
+                d.first_value = (int32_t)seen;
+                seen += h.num_values;
+                values_off_in_image = (int64_t)h.def_bytes + h.rep_bytes;
+                if (!h.is_compressed) d.codec = PST_CODEC_NONE;
+            } else {
+                throw std::runtime_error("unknown page type " + std::to_string(h.type));
+            }
+            if (d.kind != PK_DICT) {
+                switch (h.encoding) {
+                    case ENC_PLAIN: case ENC_PLAIN_DICTIONARY: case ENC_RLE_DICTIONARY: break;
+                    case ENC_RLE:
+                        if (c.type != PST_BOOLEAN) throw std::runtime_error("RLE value encoding on a non-boolean column");
+                        break;
+                    default:
+                        throw std::runtime_error("unsupported value encoding " + std::to_string(h.encoding) +
+                                                 " in column " + se.name);
+                }
+            }
+            // placement: payload as stored goes into raw; phase chosen so the value section is 16B aligned
+            int64_t phase = 0;
+            if (values_off_in_image > 0) phase = (16 - values_off_in_image % 16) % 16;
+            bool compressed = d.codec != PST_CODEC_NONE && d.comp_size > 0;
+            if (compressed) {
+                d.src_off = align_up(raw_cur, 16);
+                raw_cur = d.src_off + d.comp_size;
+                int64_t rel = align_up(scratch_cur, 16) + phase;
+                scratch_rel.push_back(rel);
+                scratch_cur = rel + d.uncomp_size + 16;  // +16: vector-store slack
+                p->compressed_pages.push_back((int32_t)p->pages.size());
+            } else {
+                d.src_off = align_up(raw_cur, 16) + phase;
+                raw_cur = d.src_off + d.comp_size + 16;  // +16: vector-load slack
+                d.img_off = d.src_off;
+                scratch_rel.push_back(-1);
+            }
+            if (d.kind != PK_DICT) p->data_pages.push_back((int32_t)p->pages.size());
+            p->payload_bytes += d.comp_size;
+            p->uncompressed_bytes += d.uncomp_size;
+            p->pages.push_back(hp);
+        }
+        if (seen != c.num_values) throw std::runtime_error("page value counts do not add up to the chunk's num_values");
+        if (dc.dict_page >= 0 && c.type == PST_BYTE_ARRAY) {
+            int64_t rel = align_up(scratch_cur, 16);
+            dict_index_rel[slot] = rel;
+            scratch_cur = rel + (int64_t)dc.dict_count * 16;
+            p->ba_dict_pages.push_back(dc.dict_page);
+        }
+    }
+
+    // ---- tables at the tail of the raw region
+    int64_t npages = (int64_t)p->pages.size();
+    p->tables_off = align_up(raw_cur, 256);
+    p->cols_off = p->tables_off;
+    p->pages_off = align_up(p->cols_off + (int64_t)sizeof(DevCol) * ncols, 64);
+    p->comp_list_off = align_up(p->pages_off + (int64_t)sizeof(DevPage) * npages, 16);
+    p->data_list_off = align_up(p->comp_list_off + 4 * (int64_t)p->compressed_pages.size(), 16);
+    p->dict_list_off = align_up(p->data_list_off + 4 * (int64_t)p->data_pages.size(), 16);
+    p->raw_bytes = align_up(p->dict_list_off + 4 * (int64_t)p->ba_dict_pages.size(), 256);
+    p->scratch_off = p->raw_bytes;
+    p->arena_bytes = align_up(p->scratch_off + scratch_cur + 256, 256);
+
+    for (size_t i = 0; i < p->pages.size(); i++)
+        if (scratch_rel[i] >= 0) p->pages[i].d.img_off = p->scratch_off + scratch_rel[i];
+
+    // ---- out region
+    int64_t out_cur = 0;
+    for (int slot = 0; slot < ncols; slot++) {
+        DevCol &dc = p->dcols[slot];
+        int64_t n = dc.num_values;
+        if (dc.dict_page >= 0) dc.dict_img_off = p->pages[dc.dict_page].d.img_off;
+        if (dict_index_rel[slot] >= 0) dc.dict_index_off = p->scratch_off + dict_index_rel[slot];
+        out_cur = align_up(out_cur, 256);
+        dc.values_off = out_cur;
+        if (dc.ptype == PST_BYTE_ARRAY) {
+            out_cur += 8 * n;
+            out_cur = align_up(out_cur, 256);
+            dc.lens_off = out_cur;
+            out_cur += 4 * n;
+        } else {
+            out_cur += (int64_t)dc.width * n;
+        }
+        if (dc.max_def > 0) {
+            out_cur = align_up(out_cur, 256);
+            dc.valid_off = out_cur;
+            out_cur += n;
+        }
+        if (dc.max_rep > 0) {
+            out_cur = align_up(out_cur, 256);
+            dc.rep_off = out_cur;
+            out_cur += n;
+            out_cur = align_up(out_cur, 256);
+            dc.def_off = out_cur;
+            out_cur += n;
+        }
+    }
+    p->out_bytes = align_up(out_cur + 16, 256);
+
+    // ---- host image of the tables
+    p->tables.assign((size_t)(p->raw_bytes - p->tables_off), 0);
+    uint8_t *t = p->tables.data();
+    memcpy(t + (p->cols_off - p->tables_off), p->dcols.data(), sizeof(DevCol) * ncols);
+    for (int64_t i = 0; i < npages; i++)
+        memcpy(t + (p->pages_off - p->tables_off) + i * (int64_t)sizeof(DevPage), &p->pages[i].d, sizeof(DevPage));
+    if (!p->compressed_pages.empty())
+        memcpy(t + (p->comp_list_off - p->tables_off), p->compressed_pages.data(), 4 * p->compressed_pages.size());
+    if (!p->data_pages.empty())
+        memcpy(t + (p->data_list_off - p->tables_off), p->data_pages.data(), 4 * p->data_pages.size());
+    if (!p->ba_dict_pages.empty())
+        memcpy(t + (p->dict_list_off - p->tables_off), p->ba_dict_pages.data(), 4 * p->ba_dict_pages.size());
+
+    // cache key: file identity + row group + column set
+    uint64_t key = 1469598103934665603ull;
+    auto mix = [&](uint64_t v) {
+        for (int i = 0; i < 8; i++) {
+            key ^= (v >> (8 * i)) & 0xff;
+            key *= 1099511628211ull;
+        }
+    };
+    for (unsigned char ch : f->path) mix(ch);
+    mix((uint64_t)f->size);
+    mix((uint64_t)f->mtime_ns);
+    mix((uint64_t)rg);
+    for (int c : p->cols) mix((uint64_t)c);
+    p->cache_key = key;
+
+    *out = p.release();
+    return 0;
+    PST_CATCH(1)
+}
+
+void pst_plan_destroy(pst_plan *p) { delete p; }
+
+int pst_plan_get_info(const pst_plan *p, pst_plan_info *out) {
+    out->num_rows = p->num_rows;
+    out->raw_bytes = p->raw_bytes;
+    out->arena_bytes = p->arena_bytes;
+    out->out_bytes = p->out_bytes;
+    out->payload_bytes = p->payload_bytes;
+    out->uncompressed_bytes = p->uncompressed_bytes;
+    out->num_pages = (int32_t)p->pages.size();
+    out->num_columns = (int32_t)p->cols.size();
+    out->num_compressed_pages = (int32_t)p->compressed_pages.size();
+    out->reserved = 0;
+    return 0;
+}
+
+int pst_plan_get_column(const pst_plan *p, int i, pst_plan_column *out) {
+    if (i < 0 || i >= (int)p->dcols.size()) {
+        set_error("plan column out of range");
+        return 1;
+    }
+    const DevCol &dc = p->dcols[i];
+    out->column = p->cols[i];
+    out->physical_type = dc.ptype;
+    out->type_length = dc.width;
+    out->max_def = dc.max_def;
+    out->max_rep = dc.max_rep;
+    out->has_dictionary = dc.dict_page >= 0;
+    out->num_values = dc.num_values;
+    out->values_off = dc.values_off;
+    out->lens_off = dc.lens_off;
+    out->valid_off = dc.valid_off;
+    out->rep_off = dc.rep_off;
+    out->def_off = dc.def_off;
+    return 0;
+}
+
+// Copies the plan's raw region image (payloads at their planned offsets + tables) into `dst` (raw_bytes bytes).
+// Host-only helper used by the staging path and by CPU tests of the planner.
+int pst_plan_fill_raw(const pst_plan *p, uint8_t *dst, int64_t first_page, int64_t last_page) {
+    int64_t n = (int64_t)p->pages.size();
+    if (first_page < 0) first_page = 0;
+    if (last_page > n) last_page = n;
+    for (int64_t i = first_page; i < last_page; i++) {
+        const HostPage &hp = p->pages[i];
+        memcpy(dst + hp.d.src_off, p->file->map + hp.file_off, (size_t)hp.d.comp_size);
+    }
+    if (first_page == 0) memcpy(dst + p->tables_off, p->tables.data(), p->tables.size());
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,53 @@
+// Internal host-side objects behind the opaque C handles.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "dev_structs.h"
+#include "parquet_meta.h"
+
+struct pst_file {
+    std::string path;
+    int fd = -1;
+    const uint8_t *map = nullptr;
+    size_t size = 0;
+    int64_t mtime_ns = 0;
+    pst::FileMeta meta;
+    std::string schema_json;
+};
+
+struct HostPage {
+    pst::DevPage d;          // what the device sees
+    int64_t file_off = 0;    // payload position in the file
+};
+
+struct pst_plan {
+    const pst_file *file = nullptr;
+    int rg = 0;
+    std::vector<int> cols;
+    std::vector<pst::DevCol> dcols;
+    std::vector<HostPage> pages;
+    std::vector<int32_t> compressed_pages;   // page indices needing decompression
+    std::vector<int32_t> data_pages;         // page indices of data pages
+    std::vector<int32_t> ba_dict_pages;      // BYTE_ARRAY dictionary pages needing an entry index
+    int64_t num_rows = 0;
+    int64_t payload_bytes = 0;
+    int64_t uncompressed_bytes = 0;
+    // arena layout
+    int64_t tables_off = 0;      // offset of the tables inside the raw region
+    int64_t cols_off = 0, pages_off = 0, comp_list_off = 0, data_list_off = 0, dict_list_off = 0;
+    int64_t raw_bytes = 0;
+    int64_t scratch_off = 0;     // == align(raw_bytes)
+    int64_t arena_bytes = 0;
+    int64_t out_bytes = 0;
+    std::vector<uint8_t> tables; // host image of the tables (copied to raw[tables_off:])
+    uint64_t cache_key = 0;
+};
+
+namespace pst {
+void set_error(const std::string &msg);
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+// Decompress at most `want` leading bytes of a raw-snappy stream (host side peek). Returns bytes produced.
+size_t snappy_peek(const uint8_t *src, size_t n, uint8_t *out, size_t want);
+}  // namespace pst

@@ -1,0 +1,154 @@
+// K9: JPEG through nvJPEG (NVIDIA library, batched API) -> interleaved RGB u8 [n, H, W, 3] in HBM.
+// Replaces cv2.imdecode (libjpeg-turbo) of CompressedImageCodec('jpeg').decode -- petastorm/codecs.py:102-116.
+// nvJPEG is dlopen'ed so libpst_b200.so loads on hosts without it; a missing library is a hard error at call time
+// (no CPU fallback).  Results differ from libjpeg-turbo by small LSB amounts (different IDCT / upsampling), which is the
+// tolerance the north star allows for this codec.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nvjpeg.h>
+
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/pst_b200.h"
+#include "host_state.h"
+
+namespace {
+
+struct NvjpegApi {
+    void *lib = nullptr;
+    decltype(&nvjpegCreateEx) CreateEx = nullptr;
+    decltype(&nvjpegCreateSimple) CreateSimple = nullptr;
+    decltype(&nvjpegDestroy) Destroy = nullptr;
+    decltype(&nvjpegJpegStateCreate) JpegStateCreate = nullptr;
+    decltype(&nvjpegJpegStateDestroy) JpegStateDestroy = nullptr;
+    decltype(&nvjpegDecodeBatchedInitialize) DecodeBatchedInitialize = nullptr;
+    decltype(&nvjpegDecodeBatched) DecodeBatched = nullptr;
+    decltype(&nvjpegGetImageInfo) GetImageInfo = nullptr;
+    bool ok = false;
+    std::string why;
+};
+
+NvjpegApi &api() {
+    static NvjpegApi a;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *names[] = {"libnvjpeg.so.12", "/usr/local/cuda/lib64/libnvjpeg.so.12", "libnvjpeg.so"};
+        for (const char *nm : names) {
+            a.lib = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+            if (a.lib) break;
+        }
+        if (!a.lib) {
+            a.why = std::string("cannot dlopen libnvjpeg: ") + (dlerror() ? dlerror() : "?");
+            return;
+        }
+#define LOAD(field, sym)                                                    \
+    a.field = reinterpret_cast<decltype(a.field)>(dlsym(a.lib, sym));       \
+    if (!a.field) {                                                         \
+        a.why = std::string("libnvjpeg lacks symbol ") + sym;               \
+        return;                                                             \
+    }
+        LOAD(CreateEx, "nvjpegCreateEx")
+        LOAD(CreateSimple, "nvjpegCreateSimple")
+        LOAD(Destroy, "nvjpegDestroy")
+        LOAD(JpegStateCreate, "nvjpegJpegStateCreate")
+        LOAD(JpegStateDestroy, "nvjpegJpegStateDestroy")
+        LOAD(DecodeBatchedInitialize, "nvjpegDecodeBatchedInitialize")
+        LOAD(DecodeBatched, "nvjpegDecodeBatched")
+        LOAD(GetImageInfo, "nvjpegGetImageInfo")
+#undef LOAD
+        a.ok = true;
+    });
+    return a;
+}
+
+struct JpegState {
+    nvjpegHandle_t handle = nullptr;
+    nvjpegJpegState_t state = nullptr;
+    int batch = 0;
+    int backend = -1;
+    std::mutex mu;
+};
+
+JpegState &jstate() {
+    static JpegState s;
+    return s;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pst_jpeg_available(void) { return api().ok ? 1 : 0; }
+
+int pst_jpeg_backend(void) { return jstate().backend; }
+
+int pst_jpeg_batch(pst_ctx *c, const uint8_t *const *host_blobs, const size_t *host_lens, int64_t n, int height,
+                   int width, uint64_t dst, uint64_t stream) {
+    (void)c;
+    try {
+        NvjpegApi &a = api();
+        if (!a.ok) throw std::runtime_error("nvJPEG unavailable: " + a.why);
+        if (n <= 0) return 0;
+        JpegState &js = jstate();
+        std::lock_guard<std::mutex> g(js.mu);
+        if (!js.handle) {
+            // GPU-assisted Huffman first (batched decode is then entirely on the device), then the hybrid backend
+            const nvjpegBackend_t order[] = {NVJPEG_BACKEND_GPU_HYBRID, NVJPEG_BACKEND_HYBRID, NVJPEG_BACKEND_DEFAULT};
+            nvjpegStatus_t st = NVJPEG_STATUS_NOT_INITIALIZED;
+            for (nvjpegBackend_t b : order) {
+                st = a.CreateEx(b, nullptr, nullptr, 0, &js.handle);
+                if (st == NVJPEG_STATUS_SUCCESS) {
+                    js.backend = (int)b;
+                    break;
+                }
+                js.handle = nullptr;
+            }
+            if (!js.handle) throw std::runtime_error("nvjpegCreateEx failed with status " + std::to_string((int)st));
+            st = a.JpegStateCreate(js.handle, &js.state);
+            if (st != NVJPEG_STATUS_SUCCESS) throw std::runtime_error("nvjpegJpegStateCreate failed " + std::to_string((int)st));
+        }
+        if (js.batch != (int)n) {
+            nvjpegStatus_t st = a.DecodeBatchedInitialize(js.handle, js.state, (int)n, 1, NVJPEG_OUTPUT_RGBI);
+            if (st != NVJPEG_STATUS_SUCCESS)
+                throw std::runtime_error("nvjpegDecodeBatchedInitialize failed " + std::to_string((int)st));
+            js.batch = (int)n;
+        }
+        // geometry check of every stream against the field shape (cheap header parse on the host)
+        for (int64_t i = 0; i < n; i++) {
+            int comps = 0;
+            nvjpegChromaSubsampling_t ss;
+            int ws[NVJPEG_MAX_COMPONENT], hs[NVJPEG_MAX_COMPONENT];
+            nvjpegStatus_t st = a.GetImageInfo(js.handle, host_blobs[i], host_lens[i], &comps, &ss, ws, hs);
+            if (st != NVJPEG_STATUS_SUCCESS)
+                throw std::runtime_error("image " + std::to_string(i) + " is not a decodable JPEG (status " + std::to_string((int)st) + ")");
+            if (ws[0] != width || hs[0] != height)
+                throw std::runtime_error("JPEG " + std::to_string(i) + " is " + std::to_string(hs[0]) + "x" + std::to_string(ws[0]) +
+                                         ", expected " + std::to_string(height) + "x" + std::to_string(width));
+        }
+        std::vector<nvjpegImage_t> outs((size_t)n);
+        uint8_t *d = (uint8_t *)dst;
+        const size_t img_bytes = (size_t)height * width * 3;
+        for (int64_t i = 0; i < n; i++) {
+            for (int k = 0; k < NVJPEG_MAX_COMPONENT; k++) {
+                outs[i].channel[k] = nullptr;
+                outs[i].pitch[k] = 0;
+            }
+            outs[i].channel[0] = d + (size_t)i * img_bytes;
+            outs[i].pitch[0] = (size_t)width * 3;
+        }
+        nvjpegStatus_t st = a.DecodeBatched(js.handle, js.state, host_blobs, host_lens, outs.data(), (cudaStream_t)stream);
+        if (st != NVJPEG_STATUS_SUCCESS) {
+            js.batch = 0;  // the batch state must be re-initialised after a failure
+            throw std::runtime_error("nvjpegDecodeBatched failed with status " + std::to_string((int)st));
+        }
+        return 0;
+    } catch (const std::exception &e) {
+        pst::set_error(e.what());
+        return 1;
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,690 @@
+// sm_100a decode kernels for Parquet pages resident in HBM.
+//
+//   k_snappy_pages   K2  raw-Snappy block decompress, one CTA (4 warps) per page
+//   k_ba_dict_index  K4  BYTE_ARRAY dictionary entry index ({offset,len} per entry)
+//   k_decode_pages   K3/K4/K5/K6  levels (RLE/bit-packed hybrid) + PLAIN / dictionary values + validity,
+//                    one CTA (256 threads) per data page
+//
+// They replace what Arrow C++ does inside `piece.read(columns=...)`
+// (reference call sites petastorm/arrow_reader_worker.py:358, petastorm/py_dict_reader_worker.py:267).
+// Formats follow the public specifications: google/snappy format_description.txt, parquet-format Encodings.md.
+//
+// All of this is byte/integer work bound by HBM bandwidth, not by math: no tensor cores.  The design rules applied are
+// coalesced 16-byte accesses (the planner places every value section 16B-aligned, see host_api.cpp), shared-memory
+// staging of run tables, and one CTA per page so that a 256 MB row-group (~600 pages) fills the 148 SMs ~4x over.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dev_structs.h"
+#include "kernels.h"
+
+namespace pst {
+
+// ---------------------------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void report_error(int32_t *status, int code, int page, int detail) {
+    if (atomicCAS(status, 0, code) == 0) {
+        status[1] = page;
+        status[2] = detail;
+    }
+}
+
+__device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t *p) {
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
+// 16 bytes starting `m` bytes into the 32-byte window {a, b}
+__device__ __forceinline__ uint4 extract16(uint4 a, uint4 b, uint32_t m) {
+    uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t q = m >> 2, s = (m & 3) * 8;
+    uint4 r;
+    // q is uniform across the cooperating threads -> no divergence; switch keeps w[] in registers
+    switch (q) {
+        case 0: r.x = __funnelshift_r(w[0], w[1], s); r.y = __funnelshift_r(w[1], w[2], s);
+                r.z = __funnelshift_r(w[2], w[3], s); r.w = __funnelshift_r(w[3], w[4], s); break;
+        case 1: r.x = __funnelshift_r(w[1], w[2], s); r.y = __funnelshift_r(w[2], w[3], s);
+                r.z = __funnelshift_r(w[3], w[4], s); r.w = __funnelshift_r(w[4], w[5], s); break;
+        case 2: r.x = __funnelshift_r(w[2], w[3], s); r.y = __funnelshift_r(w[3], w[4], s);
+                r.z = __funnelshift_r(w[4], w[5], s); r.w = __funnelshift_r(w[5], w[6], s); break;
+        default: r.x = __funnelshift_r(w[3], w[4], s); r.y = __funnelshift_r(w[4], w[5], s);
+                 r.z = __funnelshift_r(w[5], w[6], s); r.w = __funnelshift_r(w[6], w[7], s); break;
+    }
+    return r;
+}
+
+// Cooperative byte copy by `nthr` threads (tid in [0,nthr)); src and dst must not overlap.  Destination-aligned
+// 16-byte stores; source read as aligned 16-byte words and funnel-shifted, so any relative alignment runs at
+// vector width.  May read up to 15 bytes past src+n and before src (inside the same aligned 16B words) -- the planner
+// leaves that slack around every page.
+__device__ __forceinline__ void coop_copy(uint8_t *dst, const uint8_t *src, int64_t n, int tid, int nthr) {
+    if (n <= 0) return;
+    if (n < 64) {
+        for (int64_t i = tid; i < n; i += nthr) dst[i] = src[i];
+        return;
+    }
+    int64_t head = (16 - ((uintptr_t)dst & 15)) & 15;
+    for (int64_t i = tid; i < head; i += nthr) dst[i] = src[i];
+    uint8_t *d = dst + head;
+    const uint8_t *s = src + head;
+    int64_t body = (n - head) >> 4;
+    uint32_t m = (uint32_t)((uintptr_t)s & 15);
+    const uint4 *s16 = reinterpret_cast<const uint4 *>(s - m);
+    uint4 *d16 = reinterpret_cast<uint4 *>(d);
+    if (m == 0) {
+        int64_t k = tid;
+        for (; k + 3 * (int64_t)nthr < body; k += 4 * (int64_t)nthr) {
+            uint4 v0 = s16[k], v1 = s16[k + nthr], v2 = s16[k + 2 * nthr], v3 = s16[k + 3 * nthr];
+            d16[k] = v0; d16[k + nthr] = v1; d16[k + 2 * nthr] = v2; d16[k + 3 * nthr] = v3;
+        }
+        for (; k < body; k += nthr) d16[k] = s16[k];
+    } else {
+        int64_t k = tid;
+        for (; k + (int64_t)nthr < body; k += 2 * (int64_t)nthr) {
+            uint4 a0 = s16[k], b0 = s16[k + 1], a1 = s16[k + nthr], b1 = s16[k + nthr + 1];
+            d16[k] = extract16(a0, b0, m);
+            d16[k + nthr] = extract16(a1, b1, m);
+        }
+        for (; k < body; k += nthr) d16[k] = extract16(s16[k], s16[k + 1], m);
+    }
+    int64_t done = head + (body << 4);
+    for (int64_t i = done + tid; i < n; i += nthr) dst[i] = src[i];
+}
+
+__device__ __forceinline__ void coop_fill(uint8_t *dst, uint8_t v, int64_t n, int tid, int nthr) {
+    if (n <= 0) return;
+    int64_t head = (16 - ((uintptr_t)dst & 15)) & 15;
+    if (head > n) head = n;
+    for (int64_t i = tid; i < head; i += nthr) dst[i] = v;
+    int64_t body = (n - head) >> 4;
+    uint32_t w = 0x01010101u * v;
+    uint4 v4 = make_uint4(w, w, w, w);
+    uint4 *d16 = reinterpret_cast<uint4 *>(dst + head);
+    for (int64_t k = tid; k < body; k += nthr) d16[k] = v4;
+    for (int64_t i = head + (body << 4) + tid; i < n; i += nthr) dst[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K2  Snappy.  One CTA of 4 warps per page.  Every warp walks the tag stream redundantly (uniform control flow, no
+// broadcast needed); literals >= kBigLiteral bytes are split across the 4 warps, everything else is executed by
+// warp 0.  A __syncthreads() after each big literal orders the other warps' stores before warp 0's later
+// back-references; __syncwarp() orders warp 0's own element-by-element dependencies.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kSnappyThreads = 128;
+constexpr int kBigLiteral = 2048;
+
+__global__ void __launch_bounds__(kSnappyThreads)
+k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, const int32_t *__restrict__ list,
+               int n_list, int32_t *status) {
+    int li = blockIdx.x;
+    if (li >= n_list) return;
+    int pi = list[li];
+    const DevPage pg = pages[pi];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    const uint8_t *src = arena + pg.src_off;
+    uint8_t *dst = arena + pg.img_off;
+    int64_t src_n = pg.comp_size;
+    int64_t dst_n = pg.uncomp_size;
+
+    // V2 data pages: the level bytes are stored uncompressed in front of the compressed values
+    if (pg.kind == PK_DATA_V2) {
+        int64_t lv = (int64_t)pg.def_bytes + pg.rep_bytes;
+        coop_copy(dst, src, lv, threadIdx.x, kSnappyThreads);
+        src += lv; dst += lv; src_n -= lv; dst_n -= lv;
+        __syncthreads();
+        if (src_n <= 0) return;
+    }
+
+    int64_t ip = 0;
+    // preamble: varint uncompressed length
+    uint64_t ulen = 0;
+    {
+        int shift = 0;
+        for (;;) {
+            if (ip >= src_n || shift > 35) { if (threadIdx.x == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, 1); return; }
+            uint8_t b = src[ip++];
+            ulen |= (uint64_t)(b & 0x7f) << shift;
+            if (!(b & 0x80)) break;
+            shift += 7;
+        }
+    }
+    if ((int64_t)ulen != dst_n) { if (threadIdx.x == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, 2); return; }
+
+    int64_t op = 0;
+    while (ip < src_n) {
+        uint32_t tag = src[ip++];
+        uint32_t kind = tag & 3;
+        if (kind == 0) {
+            int64_t len = (tag >> 2) + 1;
+            if (len > 60) {
+                int nb = (int)len - 60;
+                if (ip + nb > src_n) { if (threadIdx.x == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, 3); return; }
+                uint32_t v = 0;
+                for (int i = 0; i < nb; i++) v |= (uint32_t)src[ip + i] << (8 * i);
+                len = (int64_t)v + 1;
+                ip += nb;
+            }
+            if (ip + len > src_n || op + len > dst_n) { if (threadIdx.x == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, 4); return; }
+            if (len >= kBigLiteral) {
+                // split in 4 parts on 16-byte boundaries of the destination
+                int64_t part = ((len >> 2) + 15) & ~(int64_t)15;
+                int64_t b0 = (int64_t)warp * part;
+                int64_t b1 = b0 + part;
+                if (b1 > len || warp == 3) b1 = len;
+                if (b0 < len) coop_copy(dst + op + b0, src + ip + b0, b1 - b0, lane, 32);
+                __syncthreads();
+            } else if (warp == 0) {
+                coop_copy(dst + op, src + ip, len, lane, 32);
+                __syncwarp();
+            }
+            ip += len;
+            op += len;
+        } else {
+            uint32_t len, offset;
+            if (kind == 1) {
+                if (ip >= src_n) { if (threadIdx.x == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, 5); return; }
+                len = ((tag >> 2) & 7) + 4;
+                offset = ((tag >> 5) << 8) | src[ip];
+                ip += 1;
+            } else if (kind == 2) {
+                if (ip + 2 > src_n) { if (threadIdx.x == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, 6); return; }
+                len = (tag >> 2) + 1;
+                offset = (uint32_t)src[ip] | ((uint32_t)src[ip + 1] << 8);
+                ip += 2;
+            } else {
+                if (ip + 4 > src_n) { if (threadIdx.x == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, 7); return; }
+                len = (tag >> 2) + 1;
+                offset = ld_u32_unaligned(src + ip);
+                ip += 4;
+            }
+            if (offset == 0 || (int64_t)offset > op || op + len > dst_n) {
+                if (threadIdx.x == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, 8);
+                return;
+            }
+            if (warp == 0) {
+                // len <= 64: at most two bytes per lane; the pattern form reads only bytes written by earlier elements
+                const uint8_t *from = dst + op - offset;
+                for (uint32_t i = lane; i < len; i += 32) {
+                    uint32_t j = (offset >= len) ? i : (i % offset);
+                    dst[op + i] = from[j];
+                }
+                __syncwarp();
+            }
+            op += len;
+        }
+    }
+    if (op != dst_n && threadIdx.x == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, 9);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K4 (BYTE_ARRAY dictionaries): {offset, len} of every entry of a PLAIN dictionary page.
+// ---------------------------------------------------------------------------------------------------------------
+struct BaDictEntry {
+    int64_t off;
+    int32_t len;
+    int32_t pad;
+};
+
+__global__ void k_ba_dict_index(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages,
+                                const DevCol *__restrict__ cols, const int32_t *__restrict__ list, int n_list,
+                                int32_t *status) {
+    int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n_list) return;
+    int pi = list[li];
+    const DevPage pg = pages[pi];
+    const DevCol col = cols[pg.col];
+    const uint8_t *img = arena + pg.img_off;
+    BaDictEntry *idx = reinterpret_cast<BaDictEntry *>(arena + col.dict_index_off);
+    int64_t pos = 0;
+    for (int i = 0; i < col.dict_count; i++) {
+        if (pos + 4 > pg.uncomp_size) { report_error(status, DE_BYTE_ARRAY_CORRUPT, pi, i); return; }
+        uint32_t len = ld_u32_unaligned(img + pos);
+        pos += 4;
+        if (pos + len > (int64_t)pg.uncomp_size) { report_error(status, DE_BYTE_ARRAY_CORRUPT, pi, i); return; }
+        idx[i].off = pg.img_off + pos;
+        idx[i].len = (int32_t)len;
+        idx[i].pad = 0;
+        pos += len;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// RLE / bit-packed hybrid stream reader (parquet Encodings.md "RLE/Bit-Packing Hybrid").
+// Thread 0 walks the run headers (inherently serial) and writes a run table into shared memory; then all threads of
+// the CTA expand table entries in parallel (bit extraction for bit-packed runs).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kDecThreads = 256;
+constexpr int kTile = 2048;       // values per tile
+constexpr int kRunCap = 256;      // run-table entries per scan round
+
+struct HybridCursor {
+    const uint8_t *p;       // next unread header byte
+    const uint8_t *end;
+    const uint8_t *bp_ptr;  // current bit-packed run: first byte of the run
+    uint32_t bp_index;      // values already consumed inside the current bit-packed run
+    uint32_t remaining;     // values left in the current run
+    uint32_t rle_value;
+    int32_t bw;
+    int32_t kind;           // 0 none, 1 RLE, 2 bit-packed
+    int32_t error;
+};
+
+struct RunEntry {
+    const uint8_t *ptr;     // bit-packed: run data; RLE: unused
+    uint32_t out_start;     // first output index (relative to this fill)
+    uint32_t count;
+    uint32_t value_or_index;  // RLE: the value; bit-packed: index of the first value inside the run
+    uint32_t is_rle;
+};
+
+struct RunTable {
+    RunEntry e[kRunCap];
+    int32_t n;
+    uint32_t filled;        // values covered by e[0..n)
+};
+
+__device__ __forceinline__ uint32_t extract_bits(const uint8_t *base, uint64_t bitoff, int bw) {
+    const uint8_t *addr = base + (bitoff >> 3);
+    uint32_t mis = (uint32_t)((uintptr_t)addr & 3);
+    const uint32_t *a = reinterpret_cast<const uint32_t *>(addr - mis);
+    uint32_t s = mis * 8 + (uint32_t)(bitoff & 7);  // <= 31
+    uint32_t w0 = a[0];
+    uint32_t w1 = (s + bw > 32) ? a[1] : 0u;
+    uint64_t v = (((uint64_t)w1 << 32) | w0) >> s;
+    uint32_t mask = bw >= 32 ? 0xffffffffu : ((1u << bw) - 1u);
+    return (uint32_t)v & mask;
+}
+
+// thread 0 only: append run entries until `want` values are covered or the table is full
+__device__ void hybrid_scan(HybridCursor &c, RunTable &t, uint32_t want) {
+    int n = 0;
+    uint32_t filled = 0;
+    while (filled < want && n < kRunCap) {
+        if (c.remaining == 0) {
+            // next run header (ULEB128)
+            uint32_t h = 0;
+            int shift = 0;
+            for (;;) {
+                if (c.p >= c.end || shift > 28) { c.error = 1; t.n = n; t.filled = filled; return; }
+                uint8_t b = *c.p++;
+                h |= (uint32_t)(b & 0x7f) << shift;
+                if (!(b & 0x80)) break;
+                shift += 7;
+            }
+            if (h & 1) {
+                uint32_t groups = h >> 1;
+                c.kind = 2;
+                c.remaining = groups * 8;
+                c.bp_ptr = c.p;
+                c.bp_index = 0;
+                c.p += (uint64_t)groups * c.bw;
+                // a writer may pad the final group past the end of the section; clamp happens via `want`
+            } else {
+                c.kind = 1;
+                c.remaining = h >> 1;
+                int nb = (c.bw + 7) >> 3;
+                uint32_t v = 0;
+                for (int i = 0; i < nb; i++) {
+                    if (c.p >= c.end) { c.error = 1; t.n = n; t.filled = filled; return; }
+                    v |= (uint32_t)(*c.p++) << (8 * i);
+                }
+                c.rle_value = v;
+            }
+            if (c.remaining == 0) continue;  // empty run (legal, useless)
+        }
+        uint32_t take = min(c.remaining, want - filled);
+        RunEntry &e = t.e[n++];
+        e.out_start = filled;
+        e.count = take;
+        if (c.kind == 1) {
+            e.is_rle = 1;
+            e.value_or_index = c.rle_value;
+            e.ptr = nullptr;
+        } else {
+            e.is_rle = 0;
+            e.value_or_index = c.bp_index;
+            e.ptr = c.bp_ptr;
+            c.bp_index += take;
+        }
+        c.remaining -= take;
+        filled += take;
+    }
+    t.n = n;
+    t.filled = filled;
+}
+
+// All threads: produce exactly `want` values of the stream into dst[0..want) (shared memory, uint32).
+// Returns false (uniformly) on a corrupt stream.
+__device__ bool hybrid_fill(HybridCursor &c, RunTable &t, uint32_t *dst, uint32_t want) {
+    uint32_t done = 0;
+    while (done < want) {
+        __syncthreads();
+        if (threadIdx.x == 0) hybrid_scan(c, t, want - done);
+        __syncthreads();
+        if (c.error || t.filled == 0) return false;
+        const int n = t.n;
+        const uint32_t filled = t.filled;
+        const int bw = c.bw;
+        int ei = 0;
+        for (uint32_t i = threadIdx.x; i < filled; i += kDecThreads) {
+            while (ei + 1 < n && t.e[ei + 1].out_start <= i) ei++;
+            const RunEntry &e = t.e[ei];
+            uint32_t v;
+            if (e.is_rle) v = e.value_or_index;
+            else v = extract_bits(e.ptr, (uint64_t)(e.value_or_index + (i - e.out_start)) * bw, bw);
+            dst[done + i] = v;
+        }
+        done += filled;
+    }
+    __syncthreads();
+    return true;
+}
+
+__device__ __forceinline__ void cursor_init(HybridCursor &c, const uint8_t *p, const uint8_t *end, int bw) {
+    c.p = p; c.end = end; c.bp_ptr = p; c.bp_index = 0; c.remaining = 0; c.rle_value = 0; c.bw = bw; c.kind = 0; c.error = 0;
+}
+
+__device__ __forceinline__ int bits_for(int max_level) {
+    int b = 0;
+    while ((1 << b) <= max_level) b++;
+    return max_level == 0 ? 0 : b;
+}
+
+// block-wide exclusive scan of one 32-bit value per (thread, item) laid out item-major: index = k*kDecThreads + tid
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += o;
+    }
+    return v;
+}
+
+struct DecodeShared {
+    HybridCursor def_c, rep_c, idx_c;
+    RunTable table;
+    uint32_t s_def[kTile];
+    uint32_t s_rep[kTile];
+    uint32_t s_idx[kTile];      // dictionary indices / boolean RLE values of the valid entries of the tile
+    uint32_t s_rank[kTile];     // exclusive rank among valid entries (tile-relative)
+    int64_t s_ba_off[kTile];    // PLAIN BYTE_ARRAY: arena offset of each valid value
+    int32_t s_ba_len[kTile];
+    uint32_t warp_sums[kDecThreads / 32];
+    const uint8_t *val_ptr;
+    const uint8_t *val_end;
+    int64_t ba_pos;             // PLAIN BYTE_ARRAY cursor (bytes into the value section)
+    uint32_t tile_valid;
+    int32_t all_valid;
+    int32_t fail;
+};
+
+template <int W>
+__device__ __forceinline__ void store_fixed(uint8_t *dst, const uint8_t *src, bool aligned) {
+    if (W == 4) {
+        uint32_t v = aligned ? *reinterpret_cast<const uint32_t *>(src) : ld_u32_unaligned(src);
+        *reinterpret_cast<uint32_t *>(dst) = v;
+    } else if (W == 8) {
+        uint64_t v;
+        if (aligned) v = *reinterpret_cast<const uint64_t *>(src);
+        else v = (uint64_t)ld_u32_unaligned(src) | ((uint64_t)ld_u32_unaligned(src + 4) << 32);
+        *reinterpret_cast<uint64_t *>(dst) = v;
+    }
+}
+
+__device__ __forceinline__ void copy_small(uint8_t *dst, const uint8_t *src, int w) {
+    for (int i = 0; i < w; i++) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(kDecThreads)
+k_decode_pages(uint8_t *__restrict__ arena, uint8_t *__restrict__ out, const DevCol *__restrict__ cols,
+               const DevPage *__restrict__ pages, const int32_t *__restrict__ list, int n_list, int32_t *status) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    DecodeShared &sh = *reinterpret_cast<DecodeShared *>(smem_raw);
+
+    int li = blockIdx.x;
+    if (li >= n_list) return;
+    const int pi = list[li];
+    const DevPage pg = pages[pi];
+    const DevCol col = cols[pg.col];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    const uint8_t *img = arena + pg.img_off;
+    const uint8_t *img_end = img + pg.uncomp_size;
+    const int W = col.width;
+    const uint32_t nvals = (uint32_t)pg.num_values;
+    const int64_t first = pg.first_value;
+
+    // ---- sections (thread 0), cursors
+    if (tid == 0) {
+        sh.fail = 0;
+        sh.all_valid = 0;
+        const uint8_t *p = img;
+        const uint8_t *rep_p = nullptr, *rep_e = nullptr, *def_p = nullptr, *def_e = nullptr;
+        int rep_bw = bits_for(col.max_rep), def_bw = bits_for(col.max_def);
+        if (pg.kind == PK_DATA_V2) {
+            rep_p = p; rep_e = p + pg.rep_bytes; p = rep_e;
+            def_p = p; def_e = p + pg.def_bytes; p = def_e;
+        } else {
+            if (col.max_rep > 0) {
+                if (pg.rep_enc == ENC_RLE) {
+                    if (p + 4 > img_end) sh.fail = 1;
+                    else { uint32_t l = ld_u32_unaligned(p); rep_p = p + 4; rep_e = rep_p + l; p = rep_e; }
+                } else sh.fail = 2;  // BIT_PACKED levels with max level > 0: deprecated, never written by parquet-mr>=1.x/arrow
+            }
+            if (col.max_def > 0 && !sh.fail) {
+                if (pg.def_enc == ENC_RLE) {
+                    if (p + 4 > img_end) sh.fail = 1;
+                    else { uint32_t l = ld_u32_unaligned(p); def_p = p + 4; def_e = def_p + l; p = def_e; }
+                } else sh.fail = 2;
+            }
+        }
+        if (p > img_end) sh.fail = 1;
+        cursor_init(sh.rep_c, rep_p, rep_e, rep_bw);
+        cursor_init(sh.def_c, def_p, def_e, def_bw);
+        sh.val_ptr = p;
+        sh.val_end = img_end;
+        sh.ba_pos = 0;
+        // all-valid shortcut: the whole page is one RLE run of max_def
+        if (!sh.fail && col.max_def > 0 && def_p && def_e > def_p) {
+            const uint8_t *q = def_p;
+            uint32_t h = 0; int shift = 0; bool ok = true;
+            for (;;) {
+                if (q >= def_e || shift > 28) { ok = false; break; }
+                uint8_t b = *q++;
+                h |= (uint32_t)(b & 0x7f) << shift;
+                if (!(b & 0x80)) break;
+                shift += 7;
+            }
+            if (ok && !(h & 1) && (h >> 1) >= nvals) {
+                int nb = (def_bw + 7) >> 3;
+                uint32_t v = 0;
+                for (int i = 0; i < nb && q < def_e; i++) v |= (uint32_t)(*q++) << (8 * i);
+                if ((int)v == col.max_def) sh.all_valid = 1;
+            }
+        }
+        if (col.max_def == 0) sh.all_valid = 1;
+        // dictionary / boolean-RLE index stream
+        bool dict_enc = pg.encoding == ENC_PLAIN_DICTIONARY || pg.encoding == ENC_RLE_DICTIONARY;
+        if (!sh.fail && dict_enc) {
+            if (p >= img_end) { if (nvals) cursor_init(sh.idx_c, p, p, 0); }
+            else { int bw = p[0]; if (bw > 32) sh.fail = 1; cursor_init(sh.idx_c, p + 1, img_end, bw); }
+            if (col.dict_img_off < 0) sh.fail = 3;
+        } else if (!sh.fail && pg.encoding == ENC_RLE) {  // boolean RLE: 4-byte length prefix, bit width 1
+            if (p + 4 > img_end) sh.fail = 1;
+            else { uint32_t l = ld_u32_unaligned(p); const uint8_t *e2 = p + 4 + l; cursor_init(sh.idx_c, p + 4, e2 < img_end ? e2 : img_end, 1); }
+        }
+    }
+    __syncthreads();
+    if (sh.fail) {
+        if (tid == 0) report_error(status, sh.fail == 2 ? DE_UNSUPPORTED_ENCODING : (sh.fail == 3 ? DE_DICT_INDEX_RANGE : DE_LEVELS_CORRUPT), pi, sh.fail);
+        return;
+    }
+
+    uint8_t *o_values = out + col.values_off;
+    uint8_t *o_valid = col.valid_off >= 0 ? out + col.valid_off : nullptr;
+    uint8_t *o_rep = col.rep_off >= 0 ? out + col.rep_off : nullptr;
+    uint8_t *o_def = col.def_off >= 0 ? out + col.def_off : nullptr;
+    const uint8_t *val_ptr = sh.val_ptr;
+    const bool all_valid = sh.all_valid != 0;
+    const bool dict_enc = pg.encoding == ENC_PLAIN_DICTIONARY || pg.encoding == ENC_RLE_DICTIONARY;
+
+    // ---- fast path: PLAIN fixed-width, no nulls, flat  ->  one vectorised copy
+    if (pg.encoding == ENC_PLAIN && all_valid && col.max_rep == 0 && col.ptype != PST_BOOLEAN_T && W > 0) {
+        int64_t nbytes = (int64_t)nvals * W;
+        if (val_ptr + nbytes > img_end) { if (tid == 0) report_error(status, DE_PAGE_OVERRUN, pi, 1); return; }
+        coop_copy(o_values + first * W, val_ptr, nbytes, tid, kDecThreads);
+        if (o_valid) coop_fill(o_valid + first, 1, nvals, tid, kDecThreads);
+        return;
+    }
+
+    const uint8_t *dict = col.dict_img_off >= 0 ? arena + col.dict_img_off : nullptr;
+    const BaDictEntry *ba_dict = col.dict_index_off >= 0 ? reinterpret_cast<const BaDictEntry *>(arena + col.dict_index_off) : nullptr;
+    const bool val_aligned = W > 0 && (((uintptr_t)val_ptr) % (W == 8 ? 8 : 4)) == 0;
+
+    uint32_t rank_base = 0;  // valid values consumed before this tile
+    for (uint32_t base = 0; base < nvals; base += kTile) {
+        const uint32_t tn = min((uint32_t)kTile, nvals - base);
+        // levels of the tile
+        if (col.max_rep > 0) {
+            if (!hybrid_fill(sh.rep_c, sh.table, sh.s_rep, tn)) { if (tid == 0) report_error(status, DE_LEVELS_CORRUPT, pi, 10); return; }
+        }
+        if (!all_valid) {
+            if (!hybrid_fill(sh.def_c, sh.table, sh.s_def, tn)) { if (tid == 0) report_error(status, DE_LEVELS_CORRUPT, pi, 11); return; }
+        }
+        // ranks: exclusive scan of validity, tile laid out item-major (i = k*256 + tid)
+        uint32_t carry = 0;
+        for (uint32_t k = 0; k < tn; k += kDecThreads) {
+            uint32_t i = k + tid;
+            uint32_t v = (i < tn) ? (all_valid ? 1u : (sh.s_def[i] == (uint32_t)col.max_def ? 1u : 0u)) : 0u;
+            uint32_t incl = warp_incl_scan(v, lane);
+            if (lane == 31) sh.warp_sums[warp] = incl;
+            __syncthreads();
+            uint32_t woff = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < kDecThreads / 32; w++) {
+                uint32_t s = sh.warp_sums[w];
+                if (w < warp) woff += s;
+                total += s;
+            }
+            if (i < tn) sh.s_rank[i] = carry + woff + incl - v;
+            carry += total;
+            __syncthreads();
+        }
+        const uint32_t tile_valid = carry;
+
+        // value-side staging for the valid entries of the tile
+        if (dict_enc || pg.encoding == ENC_RLE) {
+            if (tile_valid) {
+                if (!hybrid_fill(sh.idx_c, sh.table, sh.s_idx, tile_valid)) { if (tid == 0) report_error(status, DE_LEVELS_CORRUPT, pi, 12); return; }
+            }
+        } else if (col.ptype == PST_BYTE_ARRAY_T) {
+            // PLAIN BYTE_ARRAY: length-prefixed values; positions are a serial chain
+            if (tid == 0) {
+                int64_t pos = sh.ba_pos;
+                const int64_t lim = sh.val_end - val_ptr;
+                for (uint32_t r = 0; r < tile_valid; r++) {
+                    if (pos + 4 > lim) { sh.fail = 1; break; }
+                    uint32_t len = ld_u32_unaligned(val_ptr + pos);
+                    pos += 4;
+                    if (pos + (int64_t)len > lim) { sh.fail = 1; break; }
+                    sh.s_ba_off[r] = (val_ptr - arena) + pos;
+                    sh.s_ba_len[r] = (int32_t)len;
+                    pos += len;
+                }
+                sh.ba_pos = pos;
+            }
+            __syncthreads();
+            if (sh.fail) { if (tid == 0) report_error(status, DE_BYTE_ARRAY_CORRUPT, pi, 13); return; }
+        }
+
+        // emit
+        for (uint32_t i = tid; i < tn; i += kDecThreads) {
+            const int64_t row = first + base + i;
+            const bool valid = all_valid || sh.s_def[i] == (uint32_t)col.max_def;
+            const uint32_t r = sh.s_rank[i];            // tile-relative rank
+            const uint64_t gr = (uint64_t)rank_base + r;  // page-relative rank
+            if (o_valid) o_valid[row] = valid ? 1 : 0;
+            if (o_rep) { o_rep[row] = (uint8_t)sh.s_rep[i]; o_def[row] = (uint8_t)(all_valid ? col.max_def : sh.s_def[i]); }
+            if (col.ptype == PST_BYTE_ARRAY_T) {
+                int64_t off = 0; int32_t len = 0;
+                if (valid) {
+                    if (dict_enc) {
+                        uint32_t di = sh.s_idx[r];
+                        if (di >= (uint32_t)col.dict_count) { report_error(status, DE_DICT_INDEX_RANGE, pi, (int)di); }
+                        else { off = ba_dict[di].off; len = ba_dict[di].len; }
+                    } else { off = sh.s_ba_off[r]; len = sh.s_ba_len[r]; }
+                }
+                reinterpret_cast<int64_t *>(o_values)[row] = off;
+                reinterpret_cast<int32_t *>(out + col.lens_off)[row] = len;
+            } else if (col.ptype == PST_BOOLEAN_T) {
+                uint8_t v = 0;
+                if (valid) {
+                    if (pg.encoding == ENC_RLE) v = (uint8_t)(sh.s_idx[r] & 1);
+                    else {
+                        const uint8_t *bp = val_ptr + (gr >> 3);
+                        if (bp >= img_end) { report_error(status, DE_PAGE_OVERRUN, pi, 2); }
+                        else v = (*bp >> (gr & 7)) & 1;
+                    }
+                }
+                o_values[row] = v;
+            } else {
+                uint8_t *d = o_values + row * W;
+                if (!valid) {
+                    if (W == 4) *reinterpret_cast<uint32_t *>(d) = 0;
+                    else if (W == 8) *reinterpret_cast<uint64_t *>(d) = 0;
+                    else for (int b = 0; b < W; b++) d[b] = 0;
+                } else {
+                    const uint8_t *s;
+                    bool al;
+                    if (dict_enc) {
+                        uint32_t di = sh.s_idx[r];
+                        if (di >= (uint32_t)col.dict_count) { report_error(status, DE_DICT_INDEX_RANGE, pi, (int)di); di = 0; }
+                        s = dict + (uint64_t)di * W;
+                        al = true;  // dictionary images are placed 16B aligned
+                    } else {
+                        s = val_ptr + gr * W;
+                        al = val_aligned;
+                        if (s + W > img_end) { report_error(status, DE_PAGE_OVERRUN, pi, 3); continue; }
+                    }
+                    if (W == 4) store_fixed<4>(d, s, al);
+                    else if (W == 8) store_fixed<8>(d, s, al);
+                    else copy_small(d, s, W);
+                }
+            }
+        }
+        rank_base += tile_valid;
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------------------
+cudaError_t configure_decode_kernels() {
+    return cudaFuncSetAttribute(k_decode_pages, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeShared));
+}
+
+cudaError_t launch_snappy(uint8_t *arena, const DevPage *pages, const int32_t *list, int n, int32_t *status,
+                          cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    k_snappy_pages<<<n, kSnappyThreads, 0, s>>>(arena, pages, list, n, status);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ba_dict_index(uint8_t *arena, const DevPage *pages, const DevCol *cols, const int32_t *list, int n,
+                                 int32_t *status, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    k_ba_dict_index<<<(n + 31) / 32, 32, 0, s>>>(arena, pages, cols, list, n, status);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decode_pages(uint8_t *arena, uint8_t *out, const DevCol *cols, const DevPage *pages,
+                                const int32_t *list, int n, int32_t *status, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    size_t smem = sizeof(DecodeShared);
+    k_decode_pages<<<n, kDecThreads, smem, s>>>(arena, out, cols, pages, list, n, status);
+    return cudaGetLastError();
+}
+
+}  // namespace pst

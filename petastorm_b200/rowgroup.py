@@ -1,0 +1,219 @@
+"""Row-group decode on the device: plan (host) -> H2D of raw page bytes -> CUDA decode -> typed column tensors.
+
+This is the B200 replacement of ``piece.read(columns=...)`` (Arrow C++) that both reference workers call:
+``petastorm/arrow_reader_worker.py:358`` and ``petastorm/py_dict_reader_worker.py:267``.
+
+Ownership rule: every decoded row-group owns its HBM (``arena`` = raw page bytes + decompression scratch, ``out`` =
+decoded columns) through ordinary torch tensors; column tensors handed to users are views that keep ``out`` alive, so
+nothing is recycled under the user (the reference never reuses output buffers either - SURVEY 8b).
+"""
+import threading
+from ctypes import byref, c_int
+
+import numpy as np
+import torch
+
+from petastorm_b200 import native
+
+# parquet physical types
+BOOLEAN, INT32, INT64, INT96, FLOAT, DOUBLE, BYTE_ARRAY, FIXED_LEN_BYTE_ARRAY = range(8)
+
+_DEVICE_ERRORS = {
+    1: 'corrupt Snappy stream', 2: 'corrupt definition/repetition levels or value stream',
+    3: 'unsupported page encoding', 4: 'dictionary index out of range', 5: 'page values overrun the page',
+    6: 'NdarrayCodec blobs in one batch do not share the same .npy header', 7: 'corrupt PNG stream',
+    8: 'unsupported PNG variant (interlaced / alpha / bit depth / unexpected geometry)',
+    9: 'NGram assumes that the data is sorted by the timestamp field which is not the case',
+    10: 'corrupt BYTE_ARRAY page',
+}
+
+
+class DeviceDecodeError(RuntimeError):
+    pass
+
+
+_ctx_lock = threading.Lock()
+_contexts = {}
+_files = {}
+
+#: default budget of the pinned row-group cache (host RAM kept page-locked so that re-reading a row-group in a later
+#: epoch is one cudaMemcpyAsync); override with set_pinned_cache_bytes() before the first reader is created
+_pinned_cache_bytes = [4 << 30]
+
+
+def set_pinned_cache_bytes(nbytes):
+    _pinned_cache_bytes[0] = int(nbytes)
+
+
+def get_context(device=None):
+    """Process-wide native context of a CUDA device (created lazily)."""
+    if not torch.cuda.is_available():
+        raise native.NativeLibraryError('petastorm_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+    if device is None:
+        device = torch.cuda.current_device()
+    with _ctx_lock:
+        ctx = _contexts.get(device)
+        if ctx is None:
+            ctx = native.Context(device, _pinned_cache_bytes[0], -1)
+            _contexts[device] = ctx
+        return ctx
+
+
+def open_file(path):
+    """Cached :class:`native.ParquetFile` (mmap + parsed footer) - host only."""
+    with _ctx_lock:
+        f = _files.get(path)
+        if f is None:
+            f = native.ParquetFile(path)
+            _files[path] = f
+        return f
+
+
+def forget_files():
+    with _ctx_lock:
+        for f in _files.values():
+            f.close()
+        _files.clear()
+
+
+_TORCH_OF_PHYSICAL = {INT32: torch.int32, INT64: torch.int64, FLOAT: torch.float32, DOUBLE: torch.float64,
+                      BOOLEAN: torch.uint8}
+
+
+class DecodedColumn(object):
+    """Device-resident decode result of one leaf column of one row-group."""
+
+    __slots__ = ('leaf', 'physical_type', 'num_values', 'values', 'valid', 'offs', 'lens', 'rep', 'defs', 'max_def',
+                 'max_rep', 'arena')
+
+    def null_count(self):
+        if self.valid is None:
+            return 0
+        return int(self.num_values - int(self.valid.sum().item()))
+
+
+class DecodedRowGroup(object):
+    def __init__(self, plan, arena, out, status, stream, device):
+        self.plan = plan
+        self.arena = arena
+        self.out = out
+        self.status = status
+        self.stream = stream
+        self.device = device
+        self.num_rows = plan.info.num_rows
+        self._checked = False
+        self.event = torch.cuda.Event()
+        self.event.record(stream)
+
+    def wait(self, stream=None):
+        """Make `stream` (default: the current stream) wait for the decode; cheap, no host sync."""
+        stream = stream or torch.cuda.current_stream(self.device)
+        stream.wait_event(self.event)
+        # the buffers were allocated on the decode stream: tell the caching allocator about the consumer stream
+        self.out.record_stream(stream)
+        self.arena.record_stream(stream)
+
+    def check(self):
+        """Host-synchronises with the decode and raises if a kernel reported a malformed page."""
+        if self._checked:
+            return
+        self.event.synchronize()
+        st = self.status.cpu().tolist()
+        self._checked = True
+        if st[0] != 0:
+            raise DeviceDecodeError('{} (file {}, row-group {}, page table entry {}, detail {})'.format(
+                _DEVICE_ERRORS.get(st[0], 'device decode error %d' % st[0]), self.plan.file.path,
+                self.plan.row_group, st[1], st[2]))
+
+    def column(self, slot):
+        pc = self.plan.cols[slot]
+        n = pc.num_values
+        col = DecodedColumn()
+        col.leaf = pc.column
+        col.physical_type = pc.physical_type
+        col.num_values = n
+        col.max_def = pc.max_def
+        col.max_rep = pc.max_rep
+        col.arena = self.arena
+        col.values = col.offs = col.lens = col.valid = col.rep = col.defs = None
+        out = self.out
+        if pc.physical_type == BYTE_ARRAY:
+            col.offs = out[pc.values_off:pc.values_off + 8 * n].view(torch.int64)
+            col.lens = out[pc.lens_off:pc.lens_off + 4 * n].view(torch.int32)
+        elif pc.physical_type in _TORCH_OF_PHYSICAL:
+            dt = _TORCH_OF_PHYSICAL[pc.physical_type]
+            col.values = out[pc.values_off:pc.values_off + pc.type_length * n].view(dt)
+        else:  # INT96 / FIXED_LEN_BYTE_ARRAY: raw bytes [n, width]
+            col.values = out[pc.values_off:pc.values_off + pc.type_length * n].view(n, pc.type_length)
+        if pc.valid_off >= 0:
+            col.valid = out[pc.valid_off:pc.valid_off + n]
+        if pc.rep_off >= 0:
+            col.rep = out[pc.rep_off:pc.rep_off + n]
+            col.defs = out[pc.def_off:pc.def_off + n]
+        return col
+
+
+class RowGroupDecoder(object):
+    """Issues plan -> upload -> decode for row-groups on a side stream of one device."""
+
+    def __init__(self, device=None):
+        self.ctx = get_context(device)
+        self.device = torch.device('cuda', self.ctx.device)
+        self.stream = torch.cuda.Stream(self.device)
+        self.launches = 0
+        self.h2d_bytes = 0
+
+    def plan(self, path, row_group, leaf_columns):
+        return native.Plan(open_file(path), row_group, leaf_columns)
+
+    def upload(self, plan):
+        """H2D of a plan's raw region into a fresh arena; returns the arena tensor (async on self.stream)."""
+        with torch.cuda.stream(self.stream):
+            arena = torch.empty(plan.info.arena_bytes, dtype=torch.uint8, device=self.device)
+        native.check(native.lib.pst_plan_upload(self.ctx.handle, plan.handle, arena.data_ptr(),
+                                                self.stream.cuda_stream), 'pst_plan_upload')
+        self.h2d_bytes += plan.info.raw_bytes
+        return arena
+
+    def decode_resident(self, plan, arena, stream=None):
+        """Device decode of a plan whose raw region is already resident in `arena` (no PCIe traffic)."""
+        stream = stream or self.stream
+        with torch.cuda.stream(stream):
+            out = torch.empty(plan.info.out_bytes, dtype=torch.uint8, device=self.device)
+            status = torch.zeros(8, dtype=torch.int32, device=self.device)
+        nl = c_int(0)
+        native.check(native.lib.pst_plan_decode(self.ctx.handle, plan.handle, arena.data_ptr(), out.data_ptr(),
+                                                status.data_ptr(), stream.cuda_stream, byref(nl)), 'pst_plan_decode')
+        self.launches += nl.value
+        return DecodedRowGroup(plan, arena, out, status, stream, self.device)
+
+    def decode(self, path, row_group, leaf_columns):
+        plan = self.plan(path, row_group, leaf_columns)
+        arena = self.upload(plan)
+        return self.decode_resident(plan, arena)
+
+
+def gather_blobs_to_host(col, row_indices=None):
+    """BYTE_ARRAY column -> list of python ``bytes`` (or None) on the host.
+
+    Used for the values that cannot be tensors (strings, decimals) - the reference DataLoader rejects those as well
+    (petastorm/pytorch.py:64-66) - after the device did the decompress / level / dictionary work."""
+    offs = col.offs.cpu().numpy()
+    lens = col.lens.cpu().numpy()
+    valid = col.valid.cpu().numpy() if col.valid is not None else None
+    n = len(offs)
+    if n == 0:
+        return []
+    idx = np.arange(n) if row_indices is None else np.asarray(row_indices)
+    lo = int(offs[idx].min()) if len(idx) else 0
+    hi = int((offs[idx] + lens[idx]).max()) if len(idx) else 0
+    # one contiguous D2H of the span that holds the values (values of a page are contiguous; dictionaries small)
+    span = col.arena[lo:hi].cpu().numpy().tobytes() if hi > lo else b''
+    res = []
+    for i in idx:
+        if valid is not None and not valid[i]:
+            res.append(None)
+        else:
+            o = int(offs[i]) - lo
+            res.append(span[o:o + int(lens[i])])
+    return res

@@ -1,0 +1,291 @@
+"""GPU parity of the post-processing kernels against numpy / cv2 / hashlib restatements of the reference semantics.
+Bit-exact (integer/byte work, and IEEE fp32 for normalise)."""
+import hashlib
+import io
+import sys
+
+import numpy as np
+import pyarrow as pa
+import pyarrow.parquet as pq
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _blob_column(tmp_path, blobs, compression='none', name='blob'):
+    """Writes a single BYTE_ARRAY column, decodes it on the device and returns the DecodedColumn."""
+    import torch
+    from petastorm_b200 import rowgroup
+    path = str(tmp_path / ('%s_%s.parquet' % (name, compression)))
+    pq.write_table(pa.table({name: pa.array(blobs, type=pa.binary())}), path, compression=compression,
+                   use_dictionary=False)
+    dec = rowgroup.RowGroupDecoder()
+    d = dec.decode(path, 0, [0])
+    d.check()
+    d.wait()
+    return d.column(0), d
+
+
+def test_gather_rows():
+    import torch
+    from petastorm_b200 import device_ops as ops
+    rng = np.random.default_rng(0)
+    for shape, dt in (((1000,), np.int64), ((1000,), np.float32), ((513, 7), np.uint8), ((300, 4099), np.uint8),
+                      ((64, 32, 128), np.float16), ((100,), np.uint8), ((77, 3), np.int16)):
+        a = rng.integers(0, 255, shape).astype(dt)
+        idx = rng.permutation(shape[0])[:shape[0] - 3]
+        got = ops.gather_rows(torch.from_numpy(a).cuda(), torch.from_numpy(idx).cuda()).cpu().numpy()
+        np.testing.assert_array_equal(got, a[idx])
+
+
+def test_nulls_to_nan_and_narrow():
+    import torch
+    from petastorm_b200 import device_ops as ops, rowgroup
+    rng = np.random.default_rng(1)
+    n = 10007
+    valid = rng.integers(0, 2, n).astype(np.uint8)
+    for phys, dt in ((rowgroup.INT32, np.int32), (rowgroup.INT64, np.int64), (rowgroup.FLOAT, np.float32),
+                     (rowgroup.DOUBLE, np.float64)):
+        v = (rng.standard_normal(n) * 1e6).astype(dt)
+        if dt == np.int64:
+            v = rng.integers(-2 ** 62, 2 ** 62, n)
+        got = ops.nulls_to_nan(torch.from_numpy(v).cuda(), torch.from_numpy(valid).cuda(), phys).cpu().numpy()
+        exp = np.where(valid.astype(bool), v.astype(np.float32 if dt == np.float32 else np.float64), np.nan)
+        assert got.dtype == exp.dtype
+        np.testing.assert_array_equal(got, exp)
+    v = rng.integers(-2 ** 31, 2 ** 31 - 1, n).astype(np.int32)
+    for dt, tdt in ((np.int8, torch.int8), (np.uint8, torch.uint8), (np.int16, torch.int16), (np.uint16, torch.uint16)):
+        got = ops.narrow_int32(torch.from_numpy(v).cuda(), tdt).cpu().numpy()
+        np.testing.assert_array_equal(got.view(dt), v.astype(dt))
+
+
+def test_in_set_compact_md5():
+    import torch
+    from petastorm_b200 import device_ops as ops
+    rng = np.random.default_rng(2)
+    n = 100003
+    for dt in (np.int32, np.int64, np.int16):
+        keys = rng.integers(-1000, 30000, n).astype(dt)
+        incl = np.unique(rng.integers(-1000, 30000, 5000)).astype(np.int64)
+        mask = ops.mask_in_set(torch.from_numpy(keys).cuda(), torch.from_numpy(incl).cuda())
+        exp = np.isin(keys, incl)
+        np.testing.assert_array_equal(mask.cpu().numpy().astype(bool), exp)
+        idx = ops.mask_to_indices(mask).cpu().numpy()
+        np.testing.assert_array_equal(idx, np.nonzero(exp)[0])
+    # empty / full masks
+    z = torch.zeros(5000, dtype=torch.uint8, device='cuda')
+    assert ops.mask_to_indices(z).numel() == 0
+    o = torch.ones(5000, dtype=torch.uint8, device='cuda')
+    np.testing.assert_array_equal(ops.mask_to_indices(o).cpu().numpy(), np.arange(5000))
+
+    # in_pseudorandom_split: petastorm/predicates.py:39-41,144-182
+    keys = np.concatenate([rng.integers(-2 ** 62, 2 ** 62, 20000), np.arange(-50, 50), [0, -1, 2 ** 63 - 1, -2 ** 63]]).astype(np.int64)
+    fraction_list = [0.3, 0.4, 0.3]
+    highs = [sum(fraction_list[:i + 1]) for i in range(len(fraction_list))]
+    for subset in range(3):
+        lo = (highs[subset - 1] if subset else 0) * (sys.maxsize - 1)
+        hi = highs[subset] * (sys.maxsize - 1)
+        got = ops.mask_md5_split(torch.from_numpy(keys).cuda(), lo, hi).cpu().numpy().astype(bool)
+        exp = np.array([lo <= (int(hashlib.md5(str(np.int64(k)).encode('utf-8')).hexdigest(), 16) % sys.maxsize) < hi
+                        for k in keys])
+        np.testing.assert_array_equal(got, exp)
+    k32 = rng.integers(-2 ** 31, 2 ** 31 - 1, 5000).astype(np.int32)
+    got = ops.mask_md5_split(torch.from_numpy(k32).cuda(), 0.0, 0.5 * (sys.maxsize - 1)).cpu().numpy().astype(bool)
+    exp = np.array([(int(hashlib.md5(str(k).encode()).hexdigest(), 16) % sys.maxsize) < 0.5 * (sys.maxsize - 1) for k in k32])
+    np.testing.assert_array_equal(got, exp)
+
+
+def test_normalize_bit_exact():
+    import torch
+    from petastorm_b200 import device_ops as ops
+    rng = np.random.default_rng(3)
+    mean, std = np.float32(0.137), np.float32(1.91)
+    for src_dt in (np.float16, np.float32, np.uint8, np.int16, np.uint16, np.int32):
+        for n in (8 * 1000, 8 * 1000 + 3):
+            if src_dt in (np.float16, np.float32):
+                x = rng.standard_normal(n).astype(src_dt)
+            else:
+                x = rng.integers(0, 255, n).astype(src_dt)
+            for out_dt, tdt in ((np.float16, torch.float16), (np.float32, torch.float32)):
+                exp = ((x.astype(np.float32) - mean) / std).astype(out_dt)
+                got = ops.normalize(torch.from_numpy(x).cuda(), float(mean), float(std), tdt).cpu().numpy()
+                assert got.dtype == exp.dtype
+                np.testing.assert_array_equal(got.view(np.uint16 if out_dt == np.float16 else np.uint32),
+                                              exp.view(np.uint16 if out_dt == np.float16 else np.uint32))
+
+
+def test_ngram_known_answer():
+    """Known answer of the reference's own documentation (petastorm/ngram.py:54-83, "Case 2"): ids
+    [0,3,8,10,11,20,30], delta_threshold 4, length 2 -> windows (0,3), (8,10), (10,11)."""
+    import torch
+    from petastorm_b200 import device_ops as ops
+    ts = torch.tensor([0, 3, 8, 10, 11, 20, 30], dtype=torch.int64, device='cuda')
+    ok, status = ops.ngram_valid_starts(ts, 2, 4)
+    assert ok.cpu().tolist() == [1, 0, 1, 1, 0, 0, 0]
+    starts = ops.mask_to_indices(ok).cpu().tolist()
+    pairs = [(int(ts[s]), int(ts[s + 1])) for s in starts]
+    assert pairs == [(0, 3), (8, 10), (10, 11)]
+    assert status.cpu().tolist()[0] == 0
+    # unsorted timestamps are an error
+    ts2 = torch.tensor([0, 5, 3, 9], dtype=torch.int64, device='cuda')
+    _, st2 = ops.ngram_valid_starts(ts2, 2, 100)
+    assert st2.cpu().tolist()[0] == 9
+    # random parity against the python definition
+    rng = np.random.default_rng(4)
+    t = np.cumsum(rng.integers(0, 6, 5000)).astype(np.int64)
+    for length, delta in ((1, 0), (3, 2), (16, 4)):
+        ok, st = ops.ngram_valid_starts(torch.from_numpy(t).cuda(), length, delta)
+        exp = np.zeros(len(t), dtype=np.uint8)
+        for i in range(len(t) - length + 1):
+            w = t[i:i + length]
+            exp[i] = 1 if np.all(np.diff(w) <= delta) else 0
+        np.testing.assert_array_equal(ok.cpu().numpy(), exp)
+        rows = torch.from_numpy(rng.standard_normal((len(t), 12)).astype(np.float32)).cuda()
+        starts = ops.mask_to_indices(ok)
+        win = ops.ngram_gather(rows, starts, length).cpu().numpy()
+        rn = rows.cpu().numpy()
+        for k, s in enumerate(starts.cpu().tolist()[:200]):
+            np.testing.assert_array_equal(win[k], rn[s:s + length])
+
+
+def test_sanitize():
+    import torch
+    from petastorm_b200 import device_ops as ops
+    a = torch.arange(0, 70000, 7, dtype=torch.int32).to(torch.uint16).cuda()
+    got = ops.sanitize(a)
+    assert got.dtype == torch.int32
+    np.testing.assert_array_equal(got.cpu().numpy(), a.cpu().numpy().astype(np.int32))
+    b = torch.tensor([True, False, True], device='cuda')
+    assert ops.sanitize(b).dtype == torch.uint8 and ops.sanitize(b).cpu().tolist() == [1, 0, 1]
+
+
+@pytest.mark.parametrize('compression', ['none', 'snappy'])
+def test_npy_batch(tmp_path, compression):
+    import torch
+    from petastorm_b200 import device_ops as ops
+    rng = np.random.default_rng(5)
+    arrs = [rng.standard_normal((8, 16, 16)).astype(np.float16) for _ in range(37)]
+    blobs = []
+    for a in arrs:
+        m = io.BytesIO()
+        np.save(m, a)
+        blobs.append(m.getvalue())
+    col, d = _blob_column(tmp_path, blobs, compression)
+    hdr = len(blobs[0]) - arrs[0].nbytes
+    out, status = ops.npy_batch(col, hdr, arrs[0].nbytes, torch.float16, (8, 16, 16))
+    assert status.cpu().tolist()[0] == 0
+    np.testing.assert_array_equal(out.cpu().numpy(), np.stack(arrs))
+    # permuted subset
+    idx = torch.tensor([5, 0, 36, 7], dtype=torch.int64, device='cuda')
+    out2, _ = ops.npy_batch(col, hdr, arrs[0].nbytes, torch.float16, (8, 16, 16), idx)
+    np.testing.assert_array_equal(out2.cpu().numpy(), np.stack([arrs[i] for i in (5, 0, 36, 7)]))
+    # a blob of a different shape must be flagged
+    m = io.BytesIO()
+    np.save(m, rng.standard_normal((8, 16, 17)).astype(np.float16))
+    col3, _ = _blob_column(tmp_path, blobs[:3] + [m.getvalue()], compression, name='ragged')
+    _, st3 = ops.npy_batch(col3, hdr, arrs[0].nbytes, torch.float16, (8, 16, 16))
+    assert st3.cpu().tolist()[0] == 6
+
+
+def _png_cases():
+    import cv2
+    from PIL import Image
+    rng = np.random.default_rng(6)
+    h, w = 33, 47
+    yy, xx = np.mgrid[0:h, 0:w]
+    smooth = np.stack([(xx * 3 + yy) % 256, (xx + yy * 2) % 256, (xx * yy) % 256], -1).astype(np.uint8)
+    noise = rng.integers(0, 255, (h, w, 3), dtype=np.uint8)
+    cases = {}
+    # cv2-written (what CompressedImageCodec.encode produces: BGR order in, filter Sub)
+    for name, img in (('smooth', smooth), ('noise', noise)):
+        ok, enc = cv2.imencode('.png', img[:, :, ::-1])
+        cases['cv2_' + name] = (enc.tobytes(), img)
+    gray = smooth[:, :, 0]
+    cases['cv2_gray'] = (cv2.imencode('.png', gray)[1].tobytes(), gray)
+    g16 = (rng.integers(0, 65535, (h, w))).astype(np.uint16)
+    cases['cv2_gray16'] = (cv2.imencode('.png', g16)[1].tobytes(), g16)
+    rgb16 = rng.integers(0, 65535, (h, w, 3)).astype(np.uint16)
+    cases['cv2_rgb16'] = (cv2.imencode('.png', rgb16[:, :, ::-1])[1].tobytes(), rgb16)
+    # PIL-written: adaptive filters (Paeth/Average/Up) and dynamic Huffman with long matches
+    for name, img in (('smooth', smooth), ('noise', noise)):
+        m = io.BytesIO()
+        Image.fromarray(img).save(m, format='PNG', optimize=True)
+        cases['pil_' + name] = (m.getvalue(), img)
+    flat = np.full((h, w, 3), 200, dtype=np.uint8)
+    m = io.BytesIO()
+    Image.fromarray(flat).save(m, format='PNG')
+    cases['pil_flat'] = (m.getvalue(), flat)
+    return cases
+
+
+def test_png_batch_matches_cv2(tmp_path):
+    import cv2
+    import torch
+    from petastorm_b200 import device_ops as ops
+    cases = _png_cases()
+    for name, (blob, img) in cases.items():
+        # the oracle is cv2.imdecode + channel flip, exactly petastorm/codecs.py:102-116
+        dec = cv2.imdecode(np.frombuffer(blob, dtype=np.uint8), cv2.IMREAD_UNCHANGED)
+        exp = dec if dec.ndim == 2 else dec[:, :, (2, 1, 0)]
+        np.testing.assert_array_equal(exp, img)
+        col, d = _blob_column(tmp_path, [blob] * 5, 'snappy', name=name)
+        ch = 1 if img.ndim == 2 else 3
+        tdt = torch.uint8 if img.dtype == np.uint8 else torch.uint16
+        out, status = ops.png_batch(col, img.shape[0], img.shape[1], ch, tdt)
+        assert status.cpu().tolist()[0] == 0, (name, status.cpu().tolist())
+        got = out.cpu().numpy()
+        for k in range(5):
+            np.testing.assert_array_equal(got[k], exp, err_msg=name)
+
+
+def test_png_c1_shape(tmp_path):
+    """HelloWorldSchema image1: 128x256x3 uint8 noise, cv2-encoded (multiple IDAT chunks, stored blocks)."""
+    import cv2
+    import torch
+    from petastorm_b200 import device_ops as ops
+    rng = np.random.default_rng(1234)
+    imgs = [rng.integers(0, 255, (128, 256, 3), dtype=np.uint8) for _ in range(8)]
+    yy, xx = np.mgrid[0:128, 0:256]
+    imgs.append(np.stack([(xx + yy) % 256, (xx * 2) % 256, yy % 256], -1).astype(np.uint8))
+    blobs = [cv2.imencode('.png', im[:, :, ::-1])[1].tobytes() for im in imgs]
+    col, d = _blob_column(tmp_path, blobs, 'snappy', name='c1')
+    out, status = ops.png_batch(col, 128, 256, 3, torch.uint8)
+    assert status.cpu().tolist()[0] == 0
+    np.testing.assert_array_equal(out.cpu().numpy(), np.stack(imgs))
+
+
+def test_png_errors(tmp_path):
+    import cv2
+    import torch
+    from petastorm_b200 import device_ops as ops
+    img = np.zeros((8, 8, 3), dtype=np.uint8)
+    good = cv2.imencode('.png', img)[1].tobytes()
+    col, d = _blob_column(tmp_path, [good, good[:40] + b'\x00' * 20 + good[60:]], 'none', name='bad')
+    out, status = ops.png_batch(col, 8, 8, 3, torch.uint8)
+    assert status.cpu().tolist()[0] in (7, 8)
+    # geometry mismatch
+    col2, _ = _blob_column(tmp_path, [good], 'none', name='geom')
+    _, st2 = ops.png_batch(col2, 16, 8, 3, torch.uint8)
+    assert st2.cpu().tolist()[0] == 8
+
+
+def test_jpeg_batch_close_to_cv2():
+    """nvJPEG vs libjpeg-turbo (cv2): same streams, small LSB differences allowed (north-star tolerance)."""
+    import cv2
+    import torch
+    from petastorm_b200 import device_ops as ops
+    yy, xx = np.mgrid[0:224, 0:224]
+    rng = np.random.default_rng(7)
+    blobs, exps = [], []
+    for k in range(6):
+        img = np.stack([(xx * (k + 1) + yy) % 256, (xx + yy * 2) % 256, (xx + yy + 40 * k) % 256], -1).astype(np.float32)
+        img = cv2.GaussianBlur(img, (0, 0), 6) + rng.normal(0, 2, img.shape)
+        img = np.clip(img, 0, 255).astype(np.uint8)
+        enc = cv2.imencode('.jpeg', img[:, :, ::-1], [int(cv2.IMWRITE_JPEG_QUALITY), 80])[1].tobytes()
+        blobs.append(enc)
+        exps.append(cv2.imdecode(np.frombuffer(enc, np.uint8), cv2.IMREAD_UNCHANGED)[:, :, (2, 1, 0)])
+    out = ops.jpeg_batch(blobs, 224, 224, torch.device('cuda')).cpu().numpy().astype(np.int32)
+    exp = np.stack(exps).astype(np.int32)
+    diff = np.abs(out - exp)
+    # tolerance: mean abs error < 1 LSB, max < 16 (IDCT + chroma upsampling differences), written here on purpose
+    assert diff.mean() < 1.0 and diff.max() <= 16, (diff.mean(), diff.max())
