@@ -167,6 +167,11 @@ int pst_gather_rows(uint64_t src, uint64_t idx_i64, int64_t n_out, int64_t row_b
 int pst_npy_batch(uint64_t base, uint64_t offs_i64, uint64_t lens_i32, uint64_t row_idx_i64, int64_t n,
                   int64_t data_off, int64_t payload_bytes, uint64_t dst, uint64_t d_status, uint64_t stream);
 
+/* first k bytes of every BYTE_ARRAY value -> dst[n, k] (zero padded).  Lets the host read the .npy / PNG headers of a
+ * whole row-group with one small D2H when a field's shape is variable (None dimensions in the Unischema). */
+int pst_blob_prefix(uint64_t base, uint64_t offs_i64, uint64_t lens_i32, int64_t n, int k, uint64_t dst,
+                    uint64_t stream);
+
 /* K8: PNG (zlib inflate: stored / fixed / dynamic Huffman; filters None/Sub/Up/Average/Paeth; 8/16-bit gray, RGB,
  * palette) one image per warp.  Replaces cv2.imdecode + BGR->RGB reorder -- petastorm/codecs.py:102-116.
  * dst is [n, height, width, channels] of `sample_bytes`-byte samples in RGB order, native endianness.

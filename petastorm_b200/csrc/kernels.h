@@ -33,6 +33,8 @@ cudaError_t launch_gather_rows(const uint8_t *src, const int64_t *idx, int64_t n
 cudaError_t launch_npy_batch(const uint8_t *base, const int64_t *offs, const int32_t *lens, const int64_t *row_idx,
                              int64_t n, int64_t data_off, int64_t payload_bytes, uint8_t *dst, int32_t *status,
                              cudaStream_t s);
+cudaError_t launch_blob_prefix(const uint8_t *base, const int64_t *offs, const int32_t *lens, int64_t n, int k,
+                               uint8_t *dst, cudaStream_t s);
 cudaError_t launch_mask_in_set(const void *keys, int key_bytes, int key_unsigned, int64_t n, const int64_t *set_sorted,
                                int64_t set_n, uint8_t *mask, cudaStream_t s);
 cudaError_t launch_mask_md5_split(const void *keys, int key_bytes, int key_unsigned, int64_t n, double lo, double hi,

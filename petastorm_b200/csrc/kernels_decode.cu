@@ -656,6 +656,8 @@ k_decode_pages(uint8_t *__restrict__ arena, uint8_t *__restrict__ out, const Dev
         rank_base += tile_valid;
         __syncthreads();
     }
+    // per-column count of level entries below max_def (nulls), read by the host together with the error word
+    if (tid == 0 && nvals > rank_base) atomicAdd(&status[8 + pg.col], (int32_t)(nvals - rank_base));
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -208,6 +208,23 @@ cudaError_t launch_npy_batch(const uint8_t *base, const int64_t *offs, const int
     return cudaGetLastError();
 }
 
+// first `k` bytes of every blob -> dst[n, k] (zero padded): lets the host read .npy / PNG headers of a whole
+// row-group with one small D2H when field shapes are variable
+__global__ void k_blob_prefix(const uint8_t *__restrict__ base, const int64_t *__restrict__ offs,
+                              const int32_t *__restrict__ lens, int64_t n, int k, uint8_t *__restrict__ dst) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n * k; t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t i = t / k;
+        int b = (int)(t % k);
+        dst[t] = b < lens[i] ? base[offs[i] + b] : 0;
+    }
+}
+cudaError_t launch_blob_prefix(const uint8_t *base, const int64_t *offs, const int32_t *lens, int64_t n, int k,
+                               uint8_t *dst, cudaStream_t s) {
+    if (n <= 0 || k <= 0) return cudaSuccess;
+    k_blob_prefix<<<grid_for(n * k, kThreads), kThreads, 0, s>>>(base, offs, lens, n, k, dst);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // K11 predicates
 // ---------------------------------------------------------------------------------------------------------------

@@ -155,6 +155,16 @@ def npy_batch(col, data_off, payload_bytes, torch_dtype, shape, row_index=None):
     return out, status
 
 
+def blob_prefix(col, k):
+    """uint8 [n, k] tensor holding the first k bytes of every value of a BYTE_ARRAY column."""
+    n = col.num_values
+    out = torch.empty((n, k), dtype=torch.uint8, device=col.offs.device)
+    if n:
+        check(lib.pst_blob_prefix(col.arena.data_ptr(), col.offs.data_ptr(), col.lens.data_ptr(), n, k, out.data_ptr(),
+                                  _stream()), 'blob_prefix')
+    return out
+
+
 def png_batch(col, height, width, channels, torch_dtype, row_index=None):
     """PNG blobs of a BYTE_ARRAY column -> [n, H, W, C] (or [n, H, W]) tensor in RGB order (K8)."""
     n = col.num_values if row_index is None else row_index.numel()

@@ -1,0 +1,919 @@
+"""Row-group workers of the B200 path.
+
+:class:`GpuArrowWorker` is the counterpart of ``ArrowReaderWorker`` (petastorm/arrow_reader_worker.py:117-393, batch
+reader: one result per row-group, columns as arrays) and :class:`GpuPyDictWorker` of ``PyDictReaderWorker``
+(petastorm/py_dict_reader_worker.py:100-286, row reader: codecs decoded, optional NGram).  Both keep the reference's
+plug-in seam: ``Worker(worker_id, publish_func, args)``, ``process(piece_index, worker_predicate,
+shuffle_row_drop_partition)``, ``staticmethod new_results_queue_reader()``.
+
+What differs is *where* the work happens: ``piece.read`` becomes plan + H2D + CUDA decode
+(:mod:`petastorm_b200.rowgroup`), ``table.take`` / ``DataFrame.sample`` become a device gather, codecs become batched
+kernels, predicates become device masks + stream compaction, and results stay in HBM as torch tensors (views of the
+row-group's output buffer).  Values that cannot be tensors (strings, Decimals, dates) are materialised on the host
+after the device did the decompression / level / dictionary work - the reference DataLoader refuses them anyway.
+"""
+import datetime
+import hashlib
+from decimal import Decimal
+
+import numpy as np
+import torch
+
+from petastorm_b200 import device_ops, rowgroup
+from petastorm_b200.cache import NullCache
+from petastorm_b200.codecs import (CompressedImageCodec, CompressedNdarrayCodec, NdarrayCodec, ScalarCodec,
+                                   parse_npy_header)
+from petastorm_b200.errors import DecodeFieldError
+from petastorm_b200.rowgroup import BOOLEAN, BYTE_ARRAY, DOUBLE, FIXED_LEN_BYTE_ARRAY, FLOAT, INT32, INT64, INT96
+from petastorm_b200.unischema import integer_logical_type
+from petastorm_b200.workers_pool import EmptyResultError
+from petastorm_b200.workers_pool.worker_base import WorkerBase
+
+_TORCH_OF_NUMPY = {np.dtype('uint8'): torch.uint8, np.dtype('int8'): torch.int8, np.dtype('int16'): torch.int16,
+                   np.dtype('uint16'): torch.uint16, np.dtype('int32'): torch.int32, np.dtype('uint32'): torch.uint32,
+                   np.dtype('int64'): torch.int64, np.dtype('uint64'): torch.uint64, np.dtype('float16'): torch.float16,
+                   np.dtype('float32'): torch.float32, np.dtype('float64'): torch.float64, np.dtype('bool'): torch.bool}
+
+
+def _npify(value):
+    return value.cpu().numpy() if isinstance(value, torch.Tensor) else value
+
+
+class WorkerOptions(object):
+    """Extra, GPU-specific worker arguments appended after the reference's 12-tuple."""
+
+    def __init__(self, partitions=None, output='torch', device=None):
+        self.partitions = partitions      # etl.dataset_metadata.PartitionSet
+        self.output = output              # 'torch' (device tensors) or 'numpy' (host arrays, drop-in types)
+        self.device = device
+
+
+class _RawRowGroup(object):
+    """Decoded (still raw) columns of one row-group for a set of schema field names."""
+
+    def __init__(self, piece, decoded, file_schema, name_to_slot, partition_values, num_rows):
+        self.piece = piece
+        self.decoded = decoded
+        self.file_schema = file_schema
+        self.name_to_slot = name_to_slot
+        self.partition_values = partition_values
+        self.num_rows = num_rows
+
+
+class _GpuWorkerBase(WorkerBase):
+    def __init__(self, worker_id, publish_func, args):
+        super(_GpuWorkerBase, self).__init__(worker_id, publish_func, args)
+        self._dataset_path = args[1]
+        self._schema = args[2]
+        self._ngram = args[3]
+        self._split_pieces = args[4]
+        self._local_cache = args[5]
+        self._transform_spec = args[6]
+        self._transformed_schema = args[7]
+        self._shuffle_rows = args[9]
+        self._random_seed = args[10]
+        self._options = args[12] if len(args) > 12 and args[12] is not None else WorkerOptions()
+        self._rng = np.random.default_rng(self._random_seed)
+        self._decoder = None
+        self.rows_decoded = 0
+        self.payload_bytes = 0
+
+    # ---- device decode of the requested fields ------------------------------------------------------------------
+    def _get_decoder(self):
+        if self._decoder is None:
+            self._decoder = rowgroup.RowGroupDecoder(self._options.device)
+        return self._decoder
+
+    def _read_raw(self, piece, field_names):
+        """plan + H2D + device decode of the leaf columns behind `field_names` (partition columns excluded)."""
+        dec = self._get_decoder()
+        pfile = rowgroup.open_file(piece.path)
+        partition_names = self._options.partitions.partition_names if self._options.partitions else set()
+        leaves = pfile.schema['leaves']
+        wanted = [n for n in field_names if n not in partition_names]
+        name_to_slot, leaf_ids = {}, []
+        for name in wanted:
+            ids = [l['index'] for l in leaves if l['path'][0] == name]
+            if not ids:
+                raise ValueError('Field {} was not found in the file {}'.format(name, piece.path))
+            if len(ids) > 1:
+                raise ValueError('Field {} maps to a nested parquet structure that is not supported'.format(name))
+            name_to_slot[name] = len(leaf_ids)
+            leaf_ids.append(ids[0])
+        num_rows = pfile.row_group_num_rows(piece.row_group)
+        decoded = None
+        if leaf_ids:
+            decoded = dec.decode(piece.path, piece.row_group, leaf_ids)
+            self.payload_bytes += decoded.plan.info.payload_bytes
+        pvals = {k: v for k, v in piece.partition_keys if k in field_names}
+        return _RawRowGroup(piece, decoded, pfile.schema, name_to_slot, pvals, num_rows)
+
+    # ---- row selection ------------------------------------------------------------------------------------------
+    def _row_order(self, num_rows, shuffle_row_drop_partition, ngram_length=0):
+        """Host int64 array of source rows in output order, or None for "all rows, natural order".
+
+        Combines the within-row-group shuffle (petastorm/arrow_reader_worker.py:361-371: seeded ``Generator`` kept per
+        worker, or global ``np.random`` when the seed is None/0) with the drop-partition slice
+        ``floor(arange(n) / (n / min(n, P))) == this`` (``:386-391``; the row reader additionally borrows
+        ``length-1`` rows of the next partition for NGrams, petastorm/py_dict_reader_worker.py:276-285)."""
+        order = None
+        if self._shuffle_rows and num_rows:
+            order = self._shuffle_order(num_rows)
+        this_partition, num_partitions = shuffle_row_drop_partition
+        if num_partitions > 1 and num_rows:
+            pidx = np.floor(np.arange(num_rows) / (float(num_rows) / min(num_rows, num_partitions)))
+            if ngram_length > 1:
+                nxt = np.where(pidx >= this_partition + 1)[0]
+                if nxt.size:
+                    pidx[nxt[0:ngram_length - 1]] = this_partition
+            keep = np.nonzero(pidx == this_partition)[0]
+            order = keep if order is None else order[keep]
+        return order
+
+    def _shuffle_order(self, num_rows):
+        if self._random_seed is not None and self._random_seed != 0:
+            return self._rng.permutation(num_rows)
+        return np.random.permutation(num_rows)
+
+    def _cache_key(self, piece, piece_index):
+        path = self._dataset_path
+        path_str = ','.join(path) if isinstance(path, list) else path
+        return '{}:{}:{}'.format(hashlib.md5(path_str.encode('utf-8')).hexdigest(), piece.path, piece_index)
+
+    def _check_cache_usage(self, worker_predicate, shuffle_row_drop_partition):
+        if not isinstance(self._local_cache, NullCache):
+            if worker_predicate:
+                raise RuntimeError('Local cache is not supported together with predicates, '
+                                   'unless the dataset is partitioned by the column the predicate operates on.')
+            if shuffle_row_drop_partition[1] != 1:
+                raise RuntimeError('Local cache is not supported together with shuffle_row_drop_partitions > 1')
+
+    @staticmethod
+    def _validate_predicate_fields(worker_predicate, schema):
+        predicate_fields = set(worker_predicate.get_fields())
+        if not predicate_fields:
+            raise ValueError('At least one field name must be returned by predicate\'s get_field() method')
+        all_names = set(schema.fields.keys())
+        invalid = predicate_fields - all_names
+        if invalid:
+            raise ValueError('At least some column names requested by the predicate ({}) '
+                             'are not valid schema names: ({})'.format(', '.join(invalid), ', '.join(all_names)))
+        return predicate_fields, all_names
+
+    @property
+    def diagnostics(self):
+        d = {'rows_decoded': self.rows_decoded, 'payload_bytes': self.payload_bytes}
+        if self._decoder is not None:
+            d['gpu_launches'] = self._decoder.launches
+            d['h2d_bytes'] = self._decoder.h2d_bytes
+            d.update(self._decoder.ctx.stats())
+        return d
+
+    # ---- column materialisation helpers (shared) ----------------------------------------------------------------
+    def _partition_column(self, raw, name, count):
+        dtype = self._options.partitions.dtype_of(name)
+        value = raw.partition_values[name]
+        if dtype is np.int64:
+            return np.full(count, int(value), dtype=np.int64)
+        return np.full(count, value, dtype=np.str_)
+
+    @staticmethod
+    def _leaf_of(raw, name):
+        slot = raw.name_to_slot[name]
+        col = raw.decoded.column(slot)
+        return slot, col, raw.file_schema['leaves'][col.leaf]
+
+    @staticmethod
+    def _numeric_tensor(col, leaf):
+        """Typed device tensor of a fixed-width column, nulls still zero-filled."""
+        pt = col.physical_type
+        v = col.values
+        if pt == BOOLEAN:
+            return v.view(torch.bool)
+        if pt in (INT32, INT64):
+            bits, signed = integer_logical_type(leaf)
+            if pt == INT32 and bits in (8, 16):
+                return device_ops.narrow_int32(v, {(8, True): torch.int8, (8, False): torch.uint8,
+                                                   (16, True): torch.int16, (16, False): torch.uint16}[(bits, signed)])
+            if not signed:
+                return v.view(torch.uint32 if pt == INT32 else torch.uint64)
+            return v
+        return v
+
+    @staticmethod
+    def _decimal_from_bytes(raw_bytes, scale):
+        return Decimal(int.from_bytes(raw_bytes, 'big', signed=True)).scaleb(-scale)
+
+    def _host_objects(self, col, leaf, order):
+        """Host materialisation of the values that have no tensor form: list of str / bytes / Decimal / None."""
+        pt = col.physical_type
+        is_decimal = leaf['converted_type'] == 5 or leaf['logical_kind'] == 5
+        if pt == BYTE_ARRAY:
+            blobs = rowgroup.gather_blobs_to_host(col, order)
+            if is_decimal:
+                return [None if b is None else self._decimal_from_bytes(b, leaf['scale']) for b in blobs]
+            if leaf['converted_type'] == 0 or leaf['logical_kind'] == 1:
+                return [None if b is None else b.decode('utf-8') for b in blobs]
+            return blobs
+        vals = col.values.cpu().numpy()
+        valid = col.valid.cpu().numpy().astype(bool) if col.valid is not None else np.ones(len(vals), dtype=bool)
+        idx = np.arange(len(vals)) if order is None else order
+        if pt == FIXED_LEN_BYTE_ARRAY:
+            if is_decimal:
+                return [self._decimal_from_bytes(vals[i].tobytes(), leaf['scale']) if valid[i] else None for i in idx]
+            return [vals[i].tobytes() if valid[i] else None for i in idx]
+        if is_decimal:  # INT32 / INT64 decimals
+            return [Decimal(int(vals[i])).scaleb(-leaf['scale']) if valid[i] else None for i in idx]
+        raise ValueError('no host form for physical type {}'.format(pt))
+
+    @staticmethod
+    def _datetime_array(col, leaf, order, null_count):
+        """Host datetime64 array (timestamps keep their unit like pandas>=2, dates become datetime64[D])."""
+        vals = col.values.cpu().numpy()
+        if col.physical_type == INT96:
+            # legacy impala timestamps: 8 bytes nanos-of-day + 4 bytes julian day
+            nanos = vals[:, :8].copy().view('<i8').ravel()
+            days = vals[:, 8:].copy().view('<i4').ravel().astype(np.int64)
+            out = ((days - 2440588) * 86400 * 10 ** 9 + nanos).astype('datetime64[ns]')
+        elif leaf['converted_type'] == 6 or leaf['logical_kind'] == 6:
+            out = vals.astype('datetime64[D]')
+        else:
+            unit = {1: 'ms', 2: 'us', 3: 'ns'}.get(leaf['logical_unit'])
+            if unit is None:
+                unit = 'ms' if leaf['converted_type'] == 9 else 'us'
+            out = vals.astype('datetime64[{}]'.format(unit))
+        if null_count:
+            out = out.copy()
+            out[~col.valid.cpu().numpy().astype(bool)] = np.datetime64('NaT')
+        return out if order is None else out[order]
+
+
+def _is_temporal(leaf):
+    return (leaf['physical_type'] == INT96 or leaf['converted_type'] in (6, 9, 10) or leaf['logical_kind'] in (6, 8))
+
+
+def _is_host_only(leaf):
+    pt = leaf['physical_type']
+    is_decimal = leaf['converted_type'] == 5 or leaf['logical_kind'] == 5
+    return pt in (BYTE_ARRAY, FIXED_LEN_BYTE_ARRAY) or is_decimal
+
+
+# =====================================================================================================================
+# batch reader worker
+# =====================================================================================================================
+class GpuBatch(object):
+    """One decoded row-group of the batch reader: ``columns`` maps field name -> CUDA tensor (or host numpy array for
+    strings / decimals / datetimes).  ``wait()`` orders the consumer stream after the decode."""
+
+    def __init__(self, columns, num_rows, keepalive):
+        self.columns = columns
+        self.num_rows = num_rows
+        self._keepalive = keepalive
+
+    def wait(self):
+        for k in self._keepalive:
+            if k is not None:
+                k.wait()
+
+
+class GpuArrowResultsQueueReader(object):
+    """``read_next`` of the batch reader (petastorm/arrow_reader_worker.py:89-114): one namedtuple per row-group."""
+
+    def __init__(self, output='torch'):
+        self._output = output
+
+    @property
+    def batched_output(self):
+        return True
+
+    def read_next(self, workers_pool, schema, ngram):
+        try:
+            assert not ngram, 'ArrowReader does not support ngrams for now'
+            batch = workers_pool.get_results()
+            batch.wait()
+            cols = batch.columns
+            if self._output == 'numpy':
+                cols = {k: _npify(v) for k, v in cols.items()}
+            return schema.make_namedtuple(**cols)
+        except EmptyResultError:
+            raise StopIteration
+
+
+class GpuArrowWorker(_GpuWorkerBase):
+    def __init__(self, worker_id, publish_func, args):
+        super(GpuArrowWorker, self).__init__(worker_id, publish_func, args)
+        if self._ngram:
+            raise NotImplementedError('ngrams are not supported by ArrowReaderWorker')
+
+    @staticmethod
+    def new_results_queue_reader():
+        return GpuArrowResultsQueueReader()
+
+    def process(self, piece_index, worker_predicate, shuffle_row_drop_partition):
+        piece = self._split_pieces[piece_index]
+        self._check_cache_usage(worker_predicate, shuffle_row_drop_partition)
+        if worker_predicate:
+            batch = self._load_rows_with_predicate(piece, worker_predicate, shuffle_row_drop_partition)
+        else:
+            batch = self._local_cache.get(self._cache_key(piece, piece_index),
+                                          lambda: self._load_rows(piece, shuffle_row_drop_partition))
+        if batch is not None and batch.num_rows:
+            self.rows_decoded += batch.num_rows
+            self.publish_func(batch)
+
+    # ---- column -> batch value (semantics of convert_arrow_table_to_numpy_dict, arrow_reader_worker.py:31-86) -----
+    def _materialize(self, raw, name, field, order):
+        count = raw.num_rows if order is None else len(order)
+        if name in raw.partition_values:
+            return self._partition_column(raw, name, count)
+        slot, col, leaf = self._leaf_of(raw, name)
+        nulls = raw.decoded.null_counts[slot]
+        dev_order = None if order is None else torch.from_numpy(np.ascontiguousarray(order)).to(col.arena.device)
+        if col.max_rep > 0:
+            return self._list_column(raw, name, field, col, leaf, nulls, dev_order)
+        if _is_temporal(leaf):
+            return self._datetime_array(col, leaf, order, nulls)
+        if _is_host_only(leaf):
+            objs = self._host_objects(col, leaf, order)
+            arr = np.empty(len(objs), dtype=object)
+            arr[:] = objs
+            if leaf['physical_type'] == BYTE_ARRAY and (leaf['converted_type'] == 0 or leaf['logical_kind'] == 1):
+                return arr.astype(np.str_)  # arrow_reader_worker.py:66-67 (None becomes 'None', as upstream)
+            return arr
+        t = self._numeric_tensor(col, leaf)
+        if nulls:
+            pt = col.physical_type
+            if pt == BOOLEAN:
+                # pandas yields an object column of True/False/None
+                vals = t.cpu().numpy()
+                valid = col.valid.cpu().numpy().astype(bool)
+                arr = np.empty(len(vals), dtype=object)
+                arr[:] = [bool(v) if ok else None for v, ok in zip(vals, valid)]
+                return arr if order is None else arr[order]
+            bits, signed = integer_logical_type(leaf) if pt in (INT32, INT64) else (0, True)
+            t = device_ops.nulls_to_nan(col.values, col.valid, pt, bits, not signed)
+        if dev_order is not None:
+            t = device_ops.gather_rows(t.contiguous(), dev_order)
+        return t
+
+    def _list_column(self, raw, name, field, col, leaf, nulls, dev_order):
+        n_rows = raw.num_rows
+        n = col.num_values
+        if nulls or n_rows == 0 or n % n_rows != 0 or \
+                not device_ops.list_is_uniform(col.rep, col.defs, col.max_def, n // n_rows):
+            raise RuntimeError('Length of all values in column \'{}\' are expected to be the same length.'.format(name))
+        t = self._numeric_tensor(col, leaf).view(n_rows, n // n_rows)
+        shape = self._schema_for_shapes().fields[name].shape if name in self._schema_for_shapes().fields else ()
+        if len(shape) > 1:
+            t = t.reshape((n_rows,) + tuple(shape))
+        if dev_order is not None:
+            t = device_ops.gather_rows(t.contiguous(), dev_order)
+        return t
+
+    def _schema_for_shapes(self):
+        return self._transformed_schema if self._transform_spec else self._schema
+
+    def _build_columns(self, raw, names, order):
+        if raw.decoded is not None:
+            raw.decoded.check()   # host sync: surfaces corrupt pages and delivers the per-column null counts
+            raw.decoded.wait()
+        out = {}
+        for name in names:
+            out[name] = self._materialize(raw, name, self._schema.fields[name], order)
+        return out
+
+    def _load_rows(self, piece, shuffle_row_drop_partition):
+        names = [f.name for f in self._schema.fields.values()]
+        raw = self._read_raw(piece, names)
+        order = self._row_order(raw.num_rows, shuffle_row_drop_partition)
+        with torch.cuda.stream(self._get_decoder().stream):
+            cols = self._build_columns(raw, names, order)
+            count = raw.num_rows if order is None else len(order)
+            if self._transform_spec:
+                cols = self._apply_transform(cols, count)
+            done = torch.cuda.Event()
+            done.record()
+        return GpuBatch(cols, count, [_EventWaiter(done), raw.decoded])
+
+    def _apply_transform(self, cols, count):
+        spec = self._transform_spec
+        if spec.func:
+            if spec.device:
+                cols = spec.func(cols)
+            else:
+                cols = _host_dataframe_transform(spec.func, cols, self._get_decoder().device)
+        for name in set(cols.keys()) & set(spec.removed_fields):
+            del cols[name]
+        got, want = set(cols.keys()), set(f.name for f in self._transformed_schema.fields.values())
+        if got != want:
+            raise ValueError('Transformed result columns ({rc}) do not match required schema columns({sc})'
+                             .format(rc=','.join(got), sc=','.join(want)))
+        return {name: cols[name] for name in self._transformed_schema.fields.keys()}
+
+    def _load_rows_with_predicate(self, piece, worker_predicate, shuffle_row_drop_partition):
+        predicate_fields, all_names = self._validate_predicate_fields(worker_predicate, self._schema)
+        other_names = all_names - predicate_fields
+        decoder = self._get_decoder()
+        # 1. predicate columns first
+        raw_p = self._read_raw(piece, predicate_fields)
+        order = self._row_order(raw_p.num_rows, shuffle_row_drop_partition)
+        with torch.cuda.stream(decoder.stream):
+            pcols = self._build_columns(raw_p, sorted(predicate_fields), order)
+            mask = worker_predicate.device_mask(pcols)
+            if mask is None:
+                mask = _host_vector_predicate(worker_predicate, pcols, decoder.device)
+            keep = device_ops.mask_to_indices(mask.contiguous())  # syncs: the count decides the early exit
+            if keep.numel() == 0:
+                return None
+            keep_host = keep.cpu().numpy()
+            sel = keep_host if order is None else order[keep_host]
+            # 2. the other columns, only for matching rows
+            cols = {name: _take(pcols[name], keep, keep_host) for name in pcols}
+            raw_o = None
+            if other_names:
+                raw_o = self._read_raw(piece, other_names)
+                cols.update(self._build_columns(raw_o, sorted(other_names), sel))
+            cols = {name: cols[name] for name in self._schema.fields.keys()}
+            if self._transform_spec:
+                # upstream applies func without the removed-fields post-processing here (arrow_reader_worker.py:342-345)
+                spec = self._transform_spec
+                if spec.device:
+                    cols = spec.func(cols)
+                else:
+                    cols = _host_dataframe_transform(spec.func, cols, decoder.device)
+            done = torch.cuda.Event()
+            done.record()
+        return GpuBatch(cols, int(keep.numel()), [_EventWaiter(done), raw_p.decoded, raw_o.decoded if raw_o else None])
+
+
+class _EventWaiter(object):
+    def __init__(self, event):
+        self._event = event
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self._event)
+
+
+def _take(value, dev_index, host_index):
+    if isinstance(value, torch.Tensor):
+        return device_ops.gather_rows(value.contiguous(), dev_index)
+    return value[host_index]
+
+
+def _host_vector_predicate(predicate, cols, device):
+    """User predicate without a device form on the batch reader: upstream passes a pandas DataFrame and expects a
+    boolean Series (petastorm/arrow_reader_worker.py:315-318)."""
+    import pandas as pd
+    frame = pd.DataFrame({k: list(_npify(v)) if _npify(v).ndim > 1 else _npify(v) for k, v in cols.items()})
+    res = predicate.do_include(frame)
+    mask = np.asarray(res, dtype=bool)
+    if mask.ndim == 0:
+        mask = np.full(len(frame), bool(mask))
+    return torch.from_numpy(mask.astype(np.uint8)).to(device)
+
+
+def _host_dataframe_transform(func, cols, device):
+    """Opaque user ``TransformSpec.func`` on the batch reader: it receives a pandas DataFrame like upstream
+    (petastorm/arrow_reader_worker.py:247-277) and the returned columns go back to the device."""
+    import pandas as pd
+    data = {}
+    for k, v in cols.items():
+        a = _npify(v)
+        data[k] = list(a) if a.ndim > 1 else a
+    out = func(pd.DataFrame(data))
+    res = {}
+    for k in out.columns:
+        s = out[k]
+        a = s.values
+        if a.dtype == object and len(a) and isinstance(a[0], np.ndarray):
+            a = np.stack(list(a))
+        if isinstance(a, np.ndarray) and a.dtype in _TORCH_OF_NUMPY:
+            res[k] = torch.from_numpy(np.ascontiguousarray(a)).to(device)
+        else:
+            res[k] = np.asarray(a)
+    return res
+
+
+# =====================================================================================================================
+# row reader worker
+# =====================================================================================================================
+class GpuRowGroupRows(object):
+    """Decoded row-group of the row reader.  ``columns[name]`` is a per-row indexable: a CUDA tensor ``[n, ...]``,
+    a host numpy array, or a python list (strings, Decimals, ragged arrays, ``None`` for nulls)."""
+
+    def __init__(self, columns, num_rows, keepalive):
+        self.columns = columns
+        self.num_rows = num_rows
+        self._keepalive = keepalive
+
+    def wait(self):
+        for k in self._keepalive:
+            if k is not None:
+                k.wait()
+
+    def row(self, i, output):
+        out = {}
+        for name, col in self.columns.items():
+            v = col[i]
+            if output == 'numpy' and isinstance(v, torch.Tensor):
+                v = v.cpu().numpy()
+            out[name] = v
+        return out
+
+
+class GpuNGramWindows(object):
+    """NGram result of one row-group: window starts + the per-row columns they index into."""
+
+    def __init__(self, rows, starts, ngram):
+        self.rows = rows
+        self.starts = starts          # python list of start rows
+        self.ngram = ngram
+        self.num_rows = len(starts)
+
+    def wait(self):
+        self.rows.wait()
+
+
+class GpuPyDictResultsQueueReader(object):
+    """``read_next`` of the row reader (petastorm/py_dict_reader_worker.py:64-97): one namedtuple per row, or one
+    ``{offset: namedtuple}`` per NGram window; a row-group is buffered and handed out row by row."""
+
+    def __init__(self, output='torch'):
+        import threading
+        self._lock = threading.Lock()
+        self._current = None
+        self._next_index = 0
+        self._output = output
+
+    @property
+    def batched_output(self):
+        return False
+
+    def read_next(self, workers_pool, schema, ngram):
+        try:
+            with self._lock:
+                while self._current is None or self._next_index >= self._current.num_rows:
+                    self._current = workers_pool.get_results()
+                    self._current.wait()
+                    self._next_index = 0
+                i = self._next_index
+                self._next_index += 1
+                cur = self._current
+            if ngram:
+                start = cur.starts[i]
+                base = ngram.base_key
+                item = {}
+                for k in range(ngram.length):
+                    names = ngram.get_field_names_at_timestep(base + k)
+                    row = cur.rows.row(start + k, self._output)
+                    view = ngram.get_schema_at_timestep(schema, base + k)
+                    item[base + k] = view.make_namedtuple(**{n: row[n] for n in row if n in names})
+                return item
+            return schema.make_namedtuple(**cur.row(i, self._output))
+        except EmptyResultError:
+            raise StopIteration
+
+
+class GpuPyDictWorker(_GpuWorkerBase):
+    @staticmethod
+    def new_results_queue_reader():
+        return GpuPyDictResultsQueueReader()
+
+    def process(self, piece_index, worker_predicate, shuffle_row_drop_partition):
+        piece = self._split_pieces[piece_index]
+        self._check_cache_usage(worker_predicate, shuffle_row_drop_partition)
+        if worker_predicate:
+            rows = self._load_rows_with_predicate(piece, worker_predicate, shuffle_row_drop_partition)
+        else:
+            rows = self._local_cache.get(self._cache_key(piece, piece_index),
+                                         lambda: self._load_rows(piece, shuffle_row_drop_partition))
+        if rows is None or rows.num_rows == 0:
+            return
+        if self._ngram:
+            result = self._form_ngram(rows)
+            if result.num_rows == 0:
+                return
+            self.rows_decoded += result.num_rows
+            self.publish_func(result)
+        else:
+            self.rows_decoded += rows.num_rows
+            self.publish_func(rows)
+
+    # ---- shuffle: DataFrame.sample(frac=1, random_state=seed) (py_dict_reader_worker.py:269-270) ----------------
+    def _shuffle_order(self, num_rows):
+        # pandas' sample(frac=1, random_state=s) draws RandomState(s).permutation(n) (choice without replacement of
+        # all n rows); with seed None it uses the global numpy state
+        if self._random_seed is None:
+            return np.random.permutation(num_rows)
+        return np.random.RandomState(self._random_seed).permutation(num_rows)
+
+    # ---- per-field decode (utils.decode_row semantics, petastorm/utils.py:52-85) --------------------------------
+    def _decode_field(self, raw, name, field, order):
+        count = raw.num_rows if order is None else len(order)
+        if name in raw.partition_values:
+            value = field.numpy_dtype(raw.partition_values[name]) if field.numpy_dtype else raw.partition_values[name]
+            return [value] * count
+        slot, col, leaf = self._leaf_of(raw, name)
+        nulls = raw.decoded.null_counts[slot]
+        try:
+            codec = field.codec
+            if isinstance(codec, (NdarrayCodec, CompressedImageCodec, CompressedNdarrayCodec)) and \
+                    col.physical_type == BYTE_ARRAY:
+                return self._decode_blobs(col, field, codec, order, nulls)
+            return self._decode_scalars(col, leaf, field, order, nulls)
+        except DecodeFieldError:
+            raise
+        except Exception as e:  # pylint: disable=broad-except
+            raise DecodeFieldError('Decoding field "{}" failed'.format(name)).with_traceback(e.__traceback__)
+
+    def _decode_scalars(self, col, leaf, field, order, nulls):
+        """ScalarCodec / codec-less scalar: ``field.numpy_dtype(value)`` per row, ``None`` at nulls."""
+        np_type = field.numpy_dtype
+        if _is_temporal(leaf):
+            vals = list(self._datetime_array(col, leaf, order, nulls))
+        elif _is_host_only(leaf):
+            vals = self._host_objects(col, leaf, order)
+        else:
+            t = self._numeric_tensor(col, leaf)
+            arr = t.cpu().numpy()
+            if order is not None:
+                arr = arr[order]
+            vals = list(arr)
+            if nulls:
+                valid = col.valid.cpu().numpy().astype(bool)
+                if order is not None:
+                    valid = valid[order]
+                vals = [v if ok else None for v, ok in zip(vals, valid)]
+        cast = np_type is not None and isinstance(np_type, type) and issubclass(np_type, (np.generic, Decimal))
+        if field.codec is not None or cast:
+            if np_type is Decimal:
+                return [None if v is None else Decimal(v) for v in vals]
+            return [None if v is None else np_type(v) for v in vals]
+        return vals
+
+    def _decode_blobs(self, col, field, codec, order, nulls):
+        """NdarrayCodec / CompressedImageCodec / CompressedNdarrayCodec columns -> per-row indexable."""
+        device = col.arena.device
+        n_all = col.num_values
+        src_rows = np.arange(n_all) if order is None else np.asarray(order)
+        if nulls:
+            valid = col.valid.cpu().numpy().astype(bool)
+            present = valid[src_rows]
+        else:
+            present = np.ones(len(src_rows), dtype=bool)
+        live = src_rows[present]
+        live_dev = None
+        if order is not None or nulls:
+            live_dev = torch.from_numpy(np.ascontiguousarray(live.astype(np.int64))).to(device)
+        if isinstance(codec, CompressedNdarrayCodec):
+            blobs = rowgroup.gather_blobs_to_host(col, live)
+            dense = [codec.decode(field, b) for b in blobs]   # zip container parsing stays on the host for now
+        elif isinstance(codec, NdarrayCodec):
+            dense = self._decode_npy(col, field, live, live_dev)
+        elif codec.image_codec == 'png':
+            dense = self._decode_png(col, field, live, live_dev)
+        elif codec.image_codec in ('jpeg', 'jpg'):
+            dense = self._decode_jpeg(col, field, live)
+        else:
+            raise ValueError('unsupported image codec {}'.format(codec.image_codec))
+        if present.all():
+            return dense
+        out, k = [], 0
+        for ok in present:
+            if ok:
+                out.append(dense[k])
+                k += 1
+            else:
+                out.append(None)
+        return out
+
+    def _decode_npy(self, col, field, live, live_dev):
+        if len(live) == 0:
+            return []
+        device = col.arena.device
+        heads = device_ops.blob_prefix(col, 256).cpu().numpy()   # one small D2H for all headers of the row-group
+        groups = {}
+        for pos, r in enumerate(live):
+            b = heads[r].tobytes()
+            hl = _npy_header_len(b)
+            groups.setdefault(b[:hl] if 0 < hl <= len(b) else None, []).append(pos)
+        if len(groups) == 1 and None not in groups:
+            dtype, shape, fortran, data_off = parse_npy_header(next(iter(groups)))
+            if dtype in _TORCH_OF_NUMPY and not fortran and dtype.byteorder in ('=', '<', '|'):
+                payload = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+                out, status = device_ops.npy_batch(col, data_off, payload, _TORCH_OF_NUMPY[dtype], shape, live_dev)
+                if int(status[0].item()) == 0:
+                    return out
+        # ragged shapes / string dtypes / fortran order: decode each group; string arrays have no tensor form
+        result = [None] * len(live)
+        for head, positions in groups.items():
+            rows = live[positions]
+            ok = False
+            if head is not None:    # None: header longer than the prefix -> host decode
+                try:
+                    dtype, shape, fortran, data_off = parse_npy_header(head)
+                    ok = dtype in _TORCH_OF_NUMPY and not fortran and dtype.byteorder in ('=', '<', '|')
+                except Exception:  # pylint: disable=broad-except
+                    ok = False
+            if ok:
+                payload = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+                idx = torch.from_numpy(np.ascontiguousarray(rows.astype(np.int64))).to(device)
+                out, status = device_ops.npy_batch(col, data_off, payload, _TORCH_OF_NUMPY[dtype], shape, idx)
+                if int(status[0].item()) == 0:
+                    for k, p in enumerate(positions):
+                        result[p] = out[k]
+                    continue
+            blobs = rowgroup.gather_blobs_to_host(col, rows)
+            for p, b in zip(positions, blobs):
+                result[p] = NdarrayCodec().decode(field, b)
+        return result
+
+    def _decode_png(self, col, field, live, live_dev):
+        if len(live) == 0:
+            return []
+        device = col.arena.device
+        np_dtype = np.dtype(field.numpy_dtype)
+        shape = field.shape
+        if shape and None not in shape and len(shape) in (2, 3) and np_dtype in (np.dtype('uint8'), np.dtype('uint16')):
+            ch = shape[2] if len(shape) == 3 else 1
+            out, status = device_ops.png_batch(col, shape[0], shape[1], ch, _TORCH_OF_NUMPY[np_dtype], live_dev)
+            st = status.cpu().tolist()
+            if st[0] == 0:
+                return out
+            if st[0] == 7:
+                raise ValueError('corrupt PNG stream in row {} of the row-group'.format(st[1]))
+            # geometry differs from the schema (or unsupported variant): take the per-header path below
+        heads = device_ops.blob_prefix(col, 33).cpu().numpy()
+        groups = {}
+        for pos, r in enumerate(live):
+            h = heads[r]
+            w, hgt = int.from_bytes(h[16:20].tobytes(), 'big'), int.from_bytes(h[20:24].tobytes(), 'big')
+            groups.setdefault((hgt, w, int(h[24]), int(h[25])), []).append(pos)
+        result = [None] * len(live)
+        for (hgt, w, depth, ctype), positions in groups.items():
+            ch = {0: 1, 2: 3, 3: 3}.get(ctype)
+            if ch is None or depth not in (8, 16):
+                raise ValueError('Unexpected image dimensions. Supported dimensions are (H, W) or (H, W, 3).')
+            idx = torch.from_numpy(np.ascontiguousarray(live[positions].astype(np.int64))).to(device)
+            out, status = device_ops.png_batch(col, hgt, w, ch, torch.uint8 if depth == 8 else torch.uint16, idx)
+            st = status.cpu().tolist()
+            if st[0] != 0:
+                raise ValueError('PNG decode failed (code {}) in row {}'.format(st[0], st[1]))
+            for k, p in enumerate(positions):
+                result[p] = out[k]
+        return result
+
+    def _decode_jpeg(self, col, field, live):
+        if len(live) == 0:
+            return []
+        blobs = rowgroup.gather_blobs_to_host(col, live)
+        shape = field.shape
+        if shape and None not in shape and len(shape) == 3 and shape[2] == 3:
+            return device_ops.jpeg_batch(blobs, shape[0], shape[1], col.arena.device)
+        # variable geometry: group by the SOF dimensions
+        import struct
+        dims = []
+        for b in blobs:
+            dims.append(_jpeg_size(b))
+        result = [None] * len(blobs)
+        for d in set(dims):
+            pos = [i for i, x in enumerate(dims) if x == d]
+            out = device_ops.jpeg_batch([blobs[i] for i in pos], d[0], d[1], col.arena.device)
+            for k, p in enumerate(pos):
+                result[p] = out[k]
+        return result
+
+    # ---- row-group loads ----------------------------------------------------------------------------------------
+    def _decode_all(self, raw, names, order):
+        if raw.decoded is not None:
+            raw.decoded.check()
+            raw.decoded.wait()
+        return {name: self._decode_field(raw, name, self._schema.fields[name], order) for name in names}
+
+    def _load_rows(self, piece, shuffle_row_drop_partition):
+        names = [f.name for f in self._schema.fields.values()]
+        raw = self._read_raw(piece, names)
+        order = self._row_order(raw.num_rows, shuffle_row_drop_partition,
+                                self._ngram.length if self._ngram else 0)
+        decoder = self._get_decoder()
+        with torch.cuda.stream(decoder.stream):
+            cols = self._decode_all(raw, names, order)
+            count = raw.num_rows if order is None else len(order)
+            if self._transform_spec:
+                cols = self._apply_transform(cols, count)
+            done = torch.cuda.Event()
+            done.record()
+        return GpuRowGroupRows(cols, count, [_EventWaiter(done), raw.decoded])
+
+    def _apply_transform(self, cols, count):
+        spec = self._transform_spec
+        if spec.func:
+            if spec.device:
+                cols = spec.func(cols)
+            else:
+                # opaque user code: row dicts of host values, exactly what upstream passes
+                # (petastorm/py_dict_reader_worker.py:38-52)
+                rows = [spec.func({k: _npify(v[i]) for k, v in cols.items()}) for i in range(count)]
+                keys = list(rows[0].keys()) if rows else list(cols.keys())
+                cols = {k: [r[k] for r in rows] for k in keys}
+        for name in spec.removed_fields:
+            cols.pop(name, None)
+        return cols
+
+    def _load_rows_with_predicate(self, piece, worker_predicate, shuffle_row_drop_partition):
+        predicate_fields, all_names = self._validate_predicate_fields(worker_predicate, self._schema)
+        partition_names = self._options.partitions.partition_names if self._options.partitions else set()
+        other_names = all_names - predicate_fields - partition_names
+        decoder = self._get_decoder()
+        raw_p = self._read_raw(piece, predicate_fields)
+        order = self._row_order(raw_p.num_rows, shuffle_row_drop_partition,
+                                self._ngram.length if self._ngram else 0)
+        with torch.cuda.stream(decoder.stream):
+            pcols = self._decode_all(raw_p, sorted(predicate_fields), order)
+            count = raw_p.num_rows if order is None else len(order)
+            mask = self._predicate_mask(worker_predicate, raw_p, pcols, order, count)
+            keep_host = np.nonzero(mask)[0]
+            if len(keep_host) == 0:
+                return None
+            sel = keep_host if order is None else np.asarray(order)[keep_host]
+            cols = {}
+            for name, v in pcols.items():
+                if isinstance(v, torch.Tensor):
+                    cols[name] = device_ops.gather_rows(v.contiguous(),
+                                                        torch.from_numpy(keep_host.astype(np.int64)).to(v.device))
+                else:
+                    cols[name] = [v[i] for i in keep_host]
+            raw_o = None
+            if other_names:
+                raw_o = self._read_raw(piece, other_names)
+                cols.update(self._decode_all(raw_o, sorted(other_names), sel))
+            if self._transform_spec:
+                cols = self._apply_transform(cols, len(keep_host))
+            done = torch.cuda.Event()
+            done.record()
+        return GpuRowGroupRows(cols, len(keep_host), [_EventWaiter(done), raw_p.decoded, raw_o.decoded if raw_o else None])
+
+    def _predicate_mask(self, predicate, raw, pcols, order, count):
+        """Boolean host mask of the rows to keep.  Device form when the predicate has one for these columns."""
+        dev_cols = {}
+        for name in pcols:
+            if name in raw.partition_values:
+                continue
+            slot, col, leaf = self._leaf_of(raw, name)
+            if raw.decoded.null_counts[slot] == 0 and not _is_host_only(leaf) and not _is_temporal(leaf) and \
+                    col.max_rep == 0 and col.physical_type in (INT32, INT64):
+                t = self._numeric_tensor(col, leaf)
+                if order is not None:
+                    t = device_ops.gather_rows(t.contiguous(), torch.from_numpy(np.ascontiguousarray(order)).to(t.device))
+                dev_cols[name] = t
+        if len(dev_cols) == len(pcols):
+            mask = predicate.device_mask(dev_cols)
+            if mask is not None:
+                return mask.cpu().numpy().astype(bool)
+        # user-defined / host-only predicate: row-by-row like upstream (py_dict_reader_worker.py:232)
+        return np.array([bool(predicate.do_include({k: _npify(v[i]) for k, v in pcols.items()}))
+                         for i in range(count)], dtype=bool)
+
+    # ---- NGram --------------------------------------------------------------------------------------------------
+    def _form_ngram(self, rows):
+        ts_name = self._ngram.timestamp_field.name
+        ts = rows.columns[ts_name]
+        ts_list = [_npify(v) for v in ts] if not isinstance(ts, torch.Tensor) else None
+        if ts_list is not None and len(ts_list) and isinstance(ts_list[0], (np.integer, int)) and \
+                all(v is not None for v in ts_list):
+            ts_dev = torch.tensor(np.asarray(ts_list, dtype=np.int64), device=self._get_decoder().device)
+            with torch.cuda.stream(self._get_decoder().stream):
+                starts = self._ngram.window_starts_device(ts_dev).cpu().tolist()
+        elif isinstance(ts, torch.Tensor) and not ts.is_floating_point():
+            with torch.cuda.stream(self._get_decoder().stream):
+                starts = self._ngram.window_starts_device(ts.to(torch.int64)).cpu().tolist()
+        else:
+            starts = self._ngram.window_starts_host(ts_list if ts_list is not None else list(ts.cpu().numpy()))
+        return GpuNGramWindows(rows, starts, self._ngram)
+
+
+def _npy_header_len(prefix):
+    """Total header length (magic + version + length field + dict) of a .npy blob, 0 if it is not one."""
+    if prefix[:6] != b'\x93NUMPY':
+        return 0
+    if prefix[6] == 1:
+        return int.from_bytes(prefix[8:10], 'little') + 10
+    return int.from_bytes(prefix[8:12], 'little') + 12
+
+
+def _jpeg_size(blob):
+    """(height, width) from the SOF marker of a JPEG stream."""
+    i = 2
+    n = len(blob)
+    while i + 9 < n:
+        if blob[i] != 0xFF:
+            i += 1
+            continue
+        marker = blob[i + 1]
+        if marker in (0xC0, 0xC1, 0xC2):
+            return (int.from_bytes(blob[i + 5:i + 7], 'big'), int.from_bytes(blob[i + 7:i + 9], 'big'))
+        if marker in (0xD8, 0x01) or 0xD0 <= marker <= 0xD7:
+            i += 2
+            continue
+        i += 2 + int.from_bytes(blob[i + 2:i + 4], 'big')
+    raise ValueError('no SOF marker in JPEG stream')

@@ -102,6 +102,7 @@ class DecodedRowGroup(object):
         self.device = device
         self.num_rows = plan.info.num_rows
         self._checked = False
+        self.null_counts = None  # per plan column, filled by check()
         self.event = torch.cuda.Event()
         self.event.record(stream)
 
@@ -120,6 +121,7 @@ class DecodedRowGroup(object):
         self.event.synchronize()
         st = self.status.cpu().tolist()
         self._checked = True
+        self.null_counts = st[8:]
         if st[0] != 0:
             raise DeviceDecodeError('{} (file {}, row-group {}, page table entry {}, detail {})'.format(
                 _DEVICE_ERRORS.get(st[0], 'device decode error %d' % st[0]), self.plan.file.path,
@@ -180,7 +182,7 @@ class RowGroupDecoder(object):
         stream = stream or self.stream
         with torch.cuda.stream(stream):
             out = torch.empty(plan.info.out_bytes, dtype=torch.uint8, device=self.device)
-            status = torch.zeros(8, dtype=torch.int32, device=self.device)
+            status = torch.zeros(8 + len(plan.cols), dtype=torch.int32, device=self.device)
         nl = c_int(0)
         native.check(native.lib.pst_plan_decode(self.ctx.handle, plan.handle, arena.data_ptr(), out.data_ptr(),
                                                 status.data_ptr(), stream.cuda_stream, byref(nl)), 'pst_plan_decode')

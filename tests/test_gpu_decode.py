@@ -40,6 +40,9 @@ def _compare_flat(path, **kw):
             if len(leaf['path']) != 1:
                 continue
             exp_valid = np.asarray(exp.is_valid().to_numpy(zero_copy_only=False))
+            if pa.types.is_null(exp.type):
+                assert col.valid is not None and not col.valid.cpu().numpy().any()
+                continue
             if col.valid is not None:
                 got_valid = col.valid.cpu().numpy().astype(bool)
                 np.testing.assert_array_equal(got_valid, exp_valid, err_msg='validity of %s rg %d' % (leaf['name'], rg))
