@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the Parquet -> GPU tensor read hot path (BASELINE.json configs[1], "C2").
+
+Workload (config.workload): make_batch_reader over plain Parquet with 64 float32 + 16 int64 flat columns, Snappy,
+pyarrow defaults otherwise (v1 pages, dictionary-then-PLAIN fallback, nullable columns), ~256 MB row-groups
+(666,667 rows), consumer re-batches to 4096 rows.  A stated subset of the nominal 100 M rows is materialised
+(`--row-groups`, default 8 = 5.3 M rows = 2 GB decoded) and cycled with num_epochs.
+
+One *step* = one row-group through the hot path (plan -> raw bytes -> CUDA decode -> 4096-row batches).
+
+  value        samples/s with the raw column-chunk bytes already resident in HBM (decode kernels only), CUDA events
+  e2e          samples/s through the public API (make_batch_reader) from HOST buffers: pinned host -> H2D -> decode ->
+               D2H of one 4096-row batch of one column per step; wall clock between device synchronisations
+  roofline     HBM roofline of the dominant decode kernel, timed live with CUDA events on its launching stream
+  cpu_baseline the oracle's restatement of the reference ProcessPool + ArrowReaderWorker path on this box's cores
+               (bounded sample), rank 0 / N=1 only
+  --impl reference   times that CPU path alone with the same metric/config keys
+
+Multi-GPU (torchrun, one rank per GPU): rank 0 builds the row-group owner table, one NCCL broadcast distributes it,
+then every rank decodes only its own row-groups (weak scaling: every rank does `steps` row-groups).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ROWS_PER_GROUP = 666667          # 64*4 + 16*8 = 384 B/row -> 256 MB decoded per row-group
+N_F32, N_I64 = 64, 16
+ROW_BYTES = N_F32 * 4 + N_I64 * 8
+BATCH = 4096
+DATA_DIR = os.environ.get('PST_BENCH_DIR', '/tmp/pst_bench_c2')
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# synthetic data (np.random.default_rng(1234); float32 ~ N(0,1), int64 ~ U[0, 2^40))
+# ---------------------------------------------------------------------------------------------------------------------
+def _write_one(args):
+    path, seed, rows = args
+    import numpy as np
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    rng = np.random.default_rng(seed)
+    cols = {}
+    for i in range(N_F32):
+        cols['f%02d' % i] = rng.standard_normal(rows, dtype=np.float32)
+    for i in range(N_I64):
+        cols['i%02d' % i] = rng.integers(0, 2 ** 40, rows, dtype=np.int64)
+    pq.write_table(pa.table(cols), path + '.tmp', compression='snappy', row_group_size=rows)
+    os.replace(path + '.tmp', path)
+    return path
+
+
+def ensure_dataset(n_groups, rows=ROWS_PER_GROUP):
+    import multiprocessing as mp
+    os.makedirs(DATA_DIR, exist_ok=True)
+    todo = []
+    for g in range(n_groups):
+        p = os.path.join(DATA_DIR, 'part-%05d-r%d.parquet' % (g, rows))
+        if not os.path.exists(p):
+            todo.append((p, 1234 + g, rows))
+    # stale files of another size would change the row-group list
+    keep = set('part-%05d-r%d.parquet' % (g, rows) for g in range(n_groups))
+    for name in os.listdir(DATA_DIR):
+        if name not in keep:
+            os.remove(os.path.join(DATA_DIR, name))
+    if todo:
+        with mp.get_context('spawn').Pool(min(len(todo), 16)) as pool:
+            pool.map(_write_one, todo)
+    return 'file://' + DATA_DIR
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# clocks sampler (profiling recipe: nvidia-smi during the timed region)
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(',')]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for name, v in zip(names, parts[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: oracle port of the reference's ProcessPool + ArrowReaderWorker path
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference_throughput(url, steps, warmup, workers):
+    """rows/s of the CPU ProcessPool reader (oracle/port.py:process_pool_batches) over `steps` row-groups after
+    `warmup` row-groups (child start-up excluded by the warm-up, like petastorm/benchmark/throughput.py:68-90)."""
+    from oracle import port
+    total = warmup + steps
+    n_groups = len(port.list_pieces(url))
+    epochs = (total + n_groups - 1) // n_groups
+    gen = port.process_pool_batches(url, workers, epochs=epochs)
+    rows = 0
+    t0 = None
+    for k, batch in enumerate(gen):
+        if k == warmup:
+            t0 = time.perf_counter()
+        if k >= warmup:
+            # consumer side of the reference: re-batch to 4096 (views) -- arrow_reader_worker.py:97-111 + loader
+            n = len(batch['f00'])
+            for s in range(0, n, BATCH):
+                _ = batch['f00'][s:s + BATCH]
+            rows += n
+        if k + 1 >= total:
+            break
+    dt = time.perf_counter() - t0
+    gen.close()
+    return rows / dt, rows, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=16)
+    ap.add_argument('--warmup', type=int, default=8)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--row-groups', type=int, default=8, help='row-groups materialised per GPU box (cycled)')
+    ap.add_argument('--rows-per-group', type=int, default=ROWS_PER_GROUP)
+    ap.add_argument('--cpu-workers', type=int, default=0, help='processes of the CPU reference arm (0 = all cores, max 64)')
+    ap.add_argument('--skip-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rows_pg = args.rows_per_group
+    n_groups = max(args.row_groups, world)
+    cores = os.cpu_count() or 1
+    cpu_workers = args.cpu_workers or min(cores, 64)
+
+    workload = ('C2 make_batch_reader: {}xfloat32 + {}xint64 flat columns, Snappy, {} rows/row-group (~{} MB decoded), '
+                'batch {}; {} row-groups materialised ({} rows) and cycled').format(
+                    N_F32, N_I64, rows_pg, rows_pg * ROW_BYTES // 2 ** 20, BATCH, n_groups, n_groups * rows_pg)
+    config = {'workload': workload, 'rows_per_row_group': rows_pg, 'row_groups_materialised': n_groups,
+              'batch': BATCH, 'compression': 'snappy', 'parallelism': 'row-group shards, %d rank(s)' % world,
+              'l2_policy': 'inputs larger than L2: each step reads a distinct ~%d MB arena' % (rows_pg * ROW_BYTES // 2 ** 20)}
+
+    # ------------------------------------------------------------------------------------------------ reference arm
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        url = ensure_dataset(n_groups, rows_pg)
+        # steady state needs more row-groups than worker processes: at least 2x workers measured after >= workers warm-up
+        value, rows, dt = cpu_reference_throughput(url, max(args.steps, 2 * cpu_workers), max(args.warmup, cpu_workers),
+                                                   cpu_workers)
+        line = {'impl': 'reference', 'metric': 'samples_per_sec', 'value': value, 'unit': 'samples/s',
+                'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / max(args.steps, 2 * cpu_workers),
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+                'config': config, 'delivered_gbps': value * ROW_BYTES / 1e9,
+                'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': cpu_workers, 'kind': 'port',
+                                 'sample': '%d row-groups (%d rows) after %d warm-up row-groups, %d spawned worker '
+                                           'processes, Arrow-IPC payloads' % (args.steps, rows, args.warmup, cpu_workers)},
+                'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+        print(json.dumps(line))
+        return
+
+    # ----------------------------------------------------------------------------------------------------- B200 arm
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    if rank == 0:
+        url = ensure_dataset(n_groups, rows_pg)
+    if world > 1:
+        dist.barrier()
+    url = 'file://' + DATA_DIR
+
+    from petastorm_b200 import make_batch_reader, rowgroup, sharding
+    from petastorm_b200.etl import dataset_metadata as dm
+    rowgroup.set_pinned_cache_bytes(8 << 30)
+
+    shard_kwargs = sharding.sharded_reader_kwargs(url)          # one NCCL broadcast of the owner table
+    pieces = dm.load_row_groups(dm.ParquetDataset(DATA_DIR))
+    mine = [i for i in range(len(pieces)) if world == 1 or i % world == rank]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- (1) value: raw bytes resident in HBM, decode kernels only -------------------------------------------------
+    dec = rowgroup.RowGroupDecoder(local_rank)
+    leaves = list(range(N_F32 + N_I64))
+    plans, arenas = [], []
+    for i in mine:
+        p = dec.plan(pieces[i].path, pieces[i].row_group, leaves)
+        plans.append(p)
+        arenas.append(dec.upload(p))
+    torch.cuda.synchronize()
+    payload = sum(p.info.payload_bytes for p in plans) / len(plans)   # encoded bytes E per row-group
+    stream = dec.stream
+
+    def resident_step(k):
+        j = k % len(plans)
+        d = dec.decode_resident(plans[j], arenas[j], stream)
+        col = d.column(0).values
+        # consumer side: 4096-row batches are views of the row-group tensors (no copy)
+        nb = (col.numel() + BATCH - 1) // BATCH
+        return d, nb
+
+    for k in range(args.warmup):
+        d, _ = resident_step(k)
+    barrier()
+    launches0 = dec.launches
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    keep = []
+    barrier()
+    e0.record(stream)
+    for k in range(args.steps):
+        d, _ = resident_step(args.warmup + k)
+        keep = [d]
+    e1.record(stream)
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    keep[0].check()
+    gpu_launches = dec.launches - launches0
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    value = world * args.steps * rows_pg / (dev_ms / 1e3)
+
+    # ---- (2) roofline of the dominant kernel, per-kernel CUDA events on the launching stream ---------------------
+    from ctypes import c_float
+    from petastorm_b200 import native
+    ms_acc = np.zeros(3)
+    reps = max(4, min(args.steps, 8))
+    for k in range(reps):
+        j = k % len(plans)
+        out = torch.empty(plans[j].info.out_bytes, dtype=torch.uint8, device=dev)
+        status = torch.zeros(8 + len(leaves), dtype=torch.int32, device=dev)
+        ms3 = (c_float * 3)()
+        native.check(native.lib.pst_plan_decode_timed(dec.ctx.handle, plans[j].handle, arenas[j].data_ptr(),
+                                                      out.data_ptr(), status.data_ptr(), stream.cuda_stream, ms3))
+        ms_acc += np.array(list(ms3))
+    ms_avg = ms_acc / reps
+    names = ['k_snappy_pages', 'k_ba_dict_index', 'k_decode_pages']
+    dom = int(np.argmax(ms_avg))
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))['hbm_gbs'], 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    else:
+        peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+    algo_bytes = payload + rows_pg * ROW_BYTES          # E + D per launch (one launch = one row-group)
+    achieved = algo_bytes / (ms_avg[dom] / 1e3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': names[dom], 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': algo_bytes,
+                'kernel_ms': {n: float(m) for n, m in zip(names, ms_avg)},
+                'whole_decode_frac': algo_bytes / (float(ms_avg.sum()) / 1e3) / 1e9 / peak}
+    del arenas, plans, keep, d
+    torch.cuda.empty_cache()
+
+    # ---- (3) e2e through the public API from host buffers ----------------------------------------------------------
+    total = args.warmup + args.steps
+    epochs = (total + len(mine) - 1) // len(mine) + 1
+    host_buf = torch.empty(BATCH, dtype=torch.int64).pin_memory()
+    reader = make_batch_reader(url, shuffle_row_groups=False, num_epochs=epochs, device=local_rank, **shard_kwargs)
+    it = iter(reader)
+    h2d0 = d2h = 0
+    for k in range(args.warmup):
+        b = next(it)
+        host_buf.copy_(b.i00[:BATCH], non_blocking=True)
+    barrier()
+    h2d0 = reader.diagnostics['h2d_bytes']
+    rows_e2e = 0
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        b = next(it)                              # one decoded row-group (namedtuple of CUDA tensors)
+        n = b.f00.shape[0]
+        for s in range(0, n, BATCH):              # consumer re-batches to 4096 (views)
+            _ = b.f00[s:s + BATCH]
+        host_buf.copy_(b.i00[:BATCH], non_blocking=True)   # device -> host read of the step's result
+        torch.cuda.current_stream().synchronize()
+        d2h += host_buf.numel() * 8
+        rows_e2e += n
+    barrier()
+    wall = time.perf_counter() - t0
+    diag = reader.diagnostics
+    h2d = diag['h2d_bytes'] - h2d0
+    reader.stop()
+    reader.join()
+    tw = torch.tensor([wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+    wall = float(tw.item())
+    e2e_value = world * rows_e2e / wall
+
+    # ---- (4) CPU baseline on this box's cores (rank 0, N=1 only) ----------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu_baseline:
+        cw = cpu_workers
+        v, r, dt = cpu_reference_throughput(url, max(args.steps, 2 * cw), max(args.warmup, cw), cw)
+        cpu = {'value': v, 'unit': 'samples/s', 'cores': cw, 'kind': 'port',
+               'sample': '%d rows in %.1f s: oracle/port.py ProcessPool restatement (spawned workers, '
+                         'ParquetFile.read_row_group + take + Arrow-IPC back to the consumer), pyarrow %s' %
+                         (r, dt, __import__('pyarrow').__version__), 'host_cores': cores}
+
+    if rank == 0:
+        line = {'metric': 'samples_per_sec', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps,
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+                'config': config, 'delivered_gbps': value * ROW_BYTES / 1e9, 'roofline': roofline,
+                'cpu_baseline': cpu,
+                'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d // max(args.steps, 1),
+                        'd2h_bytes_per_step': d2h // max(args.steps, 1), 'delivered_gbps': e2e_value * ROW_BYTES / 1e9,
+                        'ms_per_step': 1e3 * wall / args.steps,
+                        'h2d_gbps': world * h2d / wall / 1e9, 'pinned_cache_hits': diag.get('pinned_cache_hits')},
+                'gpu_launches': gpu_launches, 'clocks': clocks}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -141,6 +141,11 @@ int pst_plan_upload(pst_ctx *c, pst_plan *p, uint64_t d_arena, uint64_t stream);
 int pst_plan_decode(pst_ctx *c, pst_plan *p, uint64_t d_arena, uint64_t d_out, uint64_t d_status, uint64_t stream,
                     int *launches);
 
+/* Measurement aid (bench.py roofline): the same launches with CUDA events between them on `stream`; synchronises and
+ * writes the device milliseconds of {snappy, byte-array dictionary index, page decode} to ms3[0..2]. */
+int pst_plan_decode_timed(pst_ctx *c, pst_plan *p, uint64_t d_arena, uint64_t d_out, uint64_t d_status, uint64_t stream,
+                          float *ms3);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Column post-processing kernels (all async on `stream`; pointers are device addresses).
  * ------------------------------------------------------------------------------------------------------------------ */
@@ -183,6 +188,8 @@ int pst_png_batch(uint64_t base, uint64_t offs_i64, uint64_t lens_i32, uint64_t 
 
 /* K9: JPEG through nvJPEG (library) -> interleaved RGB u8 [n, height, width, 3].  `host_blobs`/`host_lens` are host
  * pointers to the n bitstreams (nvJPEG parses Huffman tables on the host).  Replaces cv2.imdecode for '.jpeg'. */
+int pst_jpeg_available(void);  /* 1 when libnvjpeg could be dlopen'ed */
+int pst_jpeg_backend(void);    /* nvjpegBackend_t in use, -1 before the first call */
 int pst_jpeg_batch(pst_ctx *c, const uint8_t *const *host_blobs, const size_t *host_lens, int64_t n, int height,
                    int width, uint64_t dst, uint64_t stream);
 

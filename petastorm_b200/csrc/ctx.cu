@@ -295,6 +295,35 @@ int pst_plan_decode(pst_ctx *c, pst_plan *p, uint64_t d_arena, uint64_t d_out, u
     PST_CATCH(1)
 }
 
+// Same launches as pst_plan_decode with a CUDA event between them, on the launching stream; synchronises and reports
+// the device time of each kernel.  Measurement aid for bench.py's roofline numbers -- not used by the readers.
+int pst_plan_decode_timed(pst_ctx *c, pst_plan *p, uint64_t d_arena, uint64_t d_out, uint64_t d_status, uint64_t stream,
+                          float *ms3) {
+    PST_TRY
+    (void)c;
+    cudaStream_t s = (cudaStream_t)stream;
+    uint8_t *arena = (uint8_t *)d_arena;
+    const DevCol *cols = (const DevCol *)(arena + p->cols_off);
+    const DevPage *pages = (const DevPage *)(arena + p->pages_off);
+    cudaEvent_t ev[4];
+    for (auto &e : ev) ck(cudaEventCreate(&e), "cudaEventCreate");
+    ck(cudaEventRecord(ev[0], s), "record");
+    ck(launch_snappy(arena, pages, (const int32_t *)(arena + p->comp_list_off), (int)p->compressed_pages.size(),
+                     (int32_t *)d_status, s), "snappy launch");
+    ck(cudaEventRecord(ev[1], s), "record");
+    ck(launch_ba_dict_index(arena, pages, cols, (const int32_t *)(arena + p->dict_list_off),
+                            (int)p->ba_dict_pages.size(), (int32_t *)d_status, s), "dict index launch");
+    ck(cudaEventRecord(ev[2], s), "record");
+    ck(launch_decode_pages(arena, (uint8_t *)d_out, cols, pages, (const int32_t *)(arena + p->data_list_off),
+                           (int)p->data_pages.size(), (int32_t *)d_status, s), "decode launch");
+    ck(cudaEventRecord(ev[3], s), "record");
+    ck(cudaEventSynchronize(ev[3]), "sync");
+    for (int i = 0; i < 3; i++) ck(cudaEventElapsedTime(&ms3[i], ev[i], ev[i + 1]), "elapsed");
+    for (auto &e : ev) cudaEventDestroy(e);
+    return 0;
+    PST_CATCH(1)
+}
+
 // ---- post-processing wrappers -------------------------------------------------------------------------------
 #define WRAP(expr, what)              \
     PST_TRY                           \

@@ -434,6 +434,12 @@ class GpuArrowWorker(_GpuWorkerBase):
                 raw_o = self._read_raw(piece, other_names)
                 cols.update(self._build_columns(raw_o, sorted(other_names), sel))
             cols = {name: cols[name] for name in self._schema.fields.keys()}
+            if int(keep.numel()) < (raw_p.num_rows if order is None else len(order)):
+                # pandas quirk kept for parity: upstream blanks the rejected rows with None before filtering
+                # (arrow_reader_worker.py:324,331), which upcasts every integer column to float64
+                for name, v in cols.items():
+                    if isinstance(v, torch.Tensor) and not v.is_floating_point() and v.dtype != torch.bool:
+                        cols[name] = v.to(torch.float64)
             if self._transform_spec:
                 # upstream applies func without the removed-fields post-processing here (arrow_reader_worker.py:342-345)
                 spec = self._transform_spec
@@ -822,8 +828,9 @@ class GpuPyDictWorker(_GpuWorkerBase):
 
     def _load_rows_with_predicate(self, piece, worker_predicate, shuffle_row_drop_partition):
         predicate_fields, all_names = self._validate_predicate_fields(worker_predicate, self._schema)
-        partition_names = self._options.partitions.partition_names if self._options.partitions else set()
-        other_names = all_names - predicate_fields - partition_names
+        # partition columns ride along with every read upstream (legacy pyarrow appended them to each piece.read), so
+        # they stay in the second read's field set; _read_raw serves them from the piece's partition keys
+        other_names = all_names - predicate_fields
         decoder = self._get_decoder()
         raw_p = self._read_raw(piece, predicate_fields)
         order = self._row_order(raw_p.num_rows, shuffle_row_drop_partition,

@@ -83,6 +83,7 @@ _sig('pst_ctx_destroy', None, c_void_p)
 _sig('pst_ctx_stats_json', c_int, c_void_p, c_char_p, c_size_t)
 _sig('pst_plan_upload', c_int, c_void_p, c_void_p, c_uint64, c_uint64)
 _sig('pst_plan_decode', c_int, c_void_p, c_void_p, c_uint64, c_uint64, c_uint64, c_uint64, POINTER(c_int))
+_sig('pst_plan_decode_timed', c_int, c_void_p, c_void_p, c_uint64, c_uint64, c_uint64, c_uint64, POINTER(c_float))
 _sig('pst_nullable_to_f64', c_int, c_uint64, c_uint64, c_int64, c_int, c_int, c_int, c_uint64, c_uint64)
 _sig('pst_narrow_int32', c_int, c_uint64, c_int64, c_int, c_uint64, c_uint64)
 _sig('pst_gather_rows', c_int, c_uint64, c_uint64, c_int64, c_int64, c_uint64, c_uint64)
@@ -111,7 +112,7 @@ EXPORTED = [
     'pst_file_num_row_groups', 'pst_file_num_rows', 'pst_file_row_group_num_rows', 'pst_file_num_columns',
     'pst_file_schema_json', 'pst_file_kv_metadata', 'pst_file_num_kv', 'pst_file_kv_at', 'pst_file_chunk_info',
     'pst_plan_create', 'pst_plan_destroy', 'pst_plan_get_info', 'pst_plan_get_column', 'pst_plan_fill_raw',
-    'pst_ctx_create', 'pst_ctx_destroy', 'pst_ctx_stats_json', 'pst_plan_upload', 'pst_plan_decode',
+    'pst_ctx_create', 'pst_ctx_destroy', 'pst_ctx_stats_json', 'pst_plan_upload', 'pst_plan_decode', 'pst_plan_decode_timed',
     'pst_nullable_to_f64', 'pst_narrow_int32', 'pst_gather_rows', 'pst_npy_batch', 'pst_blob_prefix', 'pst_png_work_bytes',
     'pst_png_batch', 'pst_jpeg_available', 'pst_jpeg_backend', 'pst_jpeg_batch', 'pst_mask_in_set_i64',
     'pst_mask_md5_split_i64', 'pst_compact_tmp_bytes', 'pst_mask_compact', 'pst_normalize',

@@ -228,6 +228,10 @@ def numpy_dtype_of_leaf(leaf):
         if ct in (_CT_TIME_MILLIS, _CT_TIME_MICROS) or lk == 7:
             raise ValueError('time-of-day columns are not supported')
         bits, signed = integer_logical_type(leaf)
+        if not signed and bits > 8:
+            # the reference's arrow -> numpy map has no uint16/uint32/uint64 branch: such columns are reported as
+            # unsupported and dropped from the inferred schema (petastorm/unischema.py:467-502, :343-349)
+            raise ValueError('Cannot auto-create unischema due to unsupported column type uint{}'.format(bits))
         return {(8, True): np.int8, (8, False): np.uint8, (16, True): np.int16, (16, False): np.uint16,
                 (32, True): np.int32, (32, False): np.uint32, (64, True): np.int64, (64, False): np.uint64}[(bits, signed)]
     if pt == 3:
@@ -242,7 +246,7 @@ def numpy_dtype_of_leaf(leaf):
         return np.bytes_
     if pt == 7:
         if lk == 15:
-            return np.float16
+            raise ValueError('Cannot auto-create unischema due to unsupported column type halffloat')
         return np.bytes_
     raise ValueError('Cannot auto-create unischema due to unsupported column type {}'.format(pt))
 
