@@ -35,7 +35,41 @@ _TORCH_OF_NUMPY = {np.dtype('uint8'): torch.uint8, np.dtype('int8'): torch.int8,
                    np.dtype('float32'): torch.float32, np.dtype('float64'): torch.float64, np.dtype('bool'): torch.bool}
 
 
+class ScalarColumn(object):
+    """A numeric scalar column of the row reader: the device tensor (for the batched loaders) plus a lazily fetched
+    host copy that serves the per-row numpy scalars the reference hands out (``field.numpy_dtype(value)``)."""
+
+    __slots__ = ('tensor', 'np_type', '_host')
+
+    def __init__(self, tensor, np_type, host=None):
+        self.tensor = tensor
+        self.np_type = np_type
+        self._host = host
+
+    def _values(self):
+        if self._host is None:
+            self._host = self.tensor.cpu().numpy()
+        return self._host
+
+    def __len__(self):
+        return int(self.tensor.shape[0])
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return ScalarColumn(self.tensor[i], self.np_type, None if self._host is None else self._host[i])
+        v = self._values()[i]
+        return self.np_type(v) if self.np_type is not None else v
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    def take(self, dev_index):
+        return ScalarColumn(device_ops.gather_rows(self.tensor.contiguous(), dev_index), self.np_type)
+
+
 def _npify(value):
+    if isinstance(value, ScalarColumn):
+        return value._values()  # pylint: disable=protected-access
     return value.cpu().numpy() if isinstance(value, torch.Tensor) else value
 
 
@@ -555,6 +589,24 @@ class GpuPyDictResultsQueueReader(object):
     def batched_output(self):
         return False
 
+    def read_next_rowgroup(self, workers_pool):
+        """Whole (rest of the) current row-group as ``{field: column}`` with device tensors where they exist - the
+        entry point of the batched loaders (no per-row namedtuples)."""
+        try:
+            with self._lock:
+                if self._current is not None and self._next_index < self._current.num_rows:
+                    cur, start = self._current, self._next_index
+                    self._current = None
+                    cols = {k: v[start:] for k, v in cur.columns.items()}
+                else:
+                    cur = workers_pool.get_results()
+                    cur.wait()
+                    self._current = None
+                    cols = dict(cur.columns)
+            return {k: (v.tensor if isinstance(v, ScalarColumn) else v) for k, v in cols.items()}
+        except EmptyResultError:
+            raise StopIteration
+
     def read_next(self, workers_pool, schema, ngram):
         try:
             with self._lock:
@@ -641,6 +693,14 @@ class GpuPyDictWorker(_GpuWorkerBase):
             vals = self._host_objects(col, leaf, order)
         else:
             t = self._numeric_tensor(col, leaf)
+            cast_ok = np_type is not None and isinstance(np_type, type) and issubclass(np_type, np.generic)
+            if not nulls and (field.codec is None or isinstance(field.codec, ScalarCodec)) and cast_ok and \
+                    np.dtype(np_type) in _TORCH_OF_NUMPY:
+                if order is not None:
+                    t = device_ops.gather_rows(t.contiguous(), torch.from_numpy(np.ascontiguousarray(order)).to(t.device))
+                if _TORCH_OF_NUMPY[np.dtype(np_type)] != t.dtype:
+                    t = t.to(_TORCH_OF_NUMPY[np.dtype(np_type)])  # e.g. ShortType storage of a uint8 field
+                return ScalarColumn(t, np_type)
             arr = t.cpu().numpy()
             if order is not None:
                 arr = arr[order]
@@ -815,11 +875,12 @@ class GpuPyDictWorker(_GpuWorkerBase):
         spec = self._transform_spec
         if spec.func:
             if spec.device:
-                cols = spec.func(cols)
+                cols = spec.func({k: (v.tensor if isinstance(v, ScalarColumn) else v) for k, v in cols.items()})
             else:
                 # opaque user code: row dicts of host values, exactly what upstream passes
                 # (petastorm/py_dict_reader_worker.py:38-52)
-                rows = [spec.func({k: _npify(v[i]) for k, v in cols.items()}) for i in range(count)]
+                rows = [spec.func({k: _npify(v[i]) if not isinstance(v, ScalarColumn) else v[i] for k, v in cols.items()})
+                        for i in range(count)]
                 keys = list(rows[0].keys()) if rows else list(cols.keys())
                 cols = {k: [r[k] for r in rows] for k in keys}
         for name in spec.removed_fields:
@@ -845,7 +906,9 @@ class GpuPyDictWorker(_GpuWorkerBase):
             sel = keep_host if order is None else np.asarray(order)[keep_host]
             cols = {}
             for name, v in pcols.items():
-                if isinstance(v, torch.Tensor):
+                if isinstance(v, ScalarColumn):
+                    cols[name] = v.take(torch.from_numpy(keep_host.astype(np.int64)).to(v.tensor.device))
+                elif isinstance(v, torch.Tensor):
                     cols[name] = device_ops.gather_rows(v.contiguous(),
                                                         torch.from_numpy(keep_host.astype(np.int64)).to(v.device))
                 else:
@@ -878,13 +941,16 @@ class GpuPyDictWorker(_GpuWorkerBase):
             if mask is not None:
                 return mask.cpu().numpy().astype(bool)
         # user-defined / host-only predicate: row-by-row like upstream (py_dict_reader_worker.py:232)
-        return np.array([bool(predicate.do_include({k: _npify(v[i]) for k, v in pcols.items()}))
+        return np.array([bool(predicate.do_include({k: (v[i] if isinstance(v, ScalarColumn) else _npify(v[i]))
+                                                      for k, v in pcols.items()}))
                          for i in range(count)], dtype=bool)
 
     # ---- NGram --------------------------------------------------------------------------------------------------
     def _form_ngram(self, rows):
         ts_name = self._ngram.timestamp_field.name
         ts = rows.columns[ts_name]
+        if isinstance(ts, ScalarColumn):
+            ts = ts.tensor
         ts_list = [_npify(v) for v in ts] if not isinstance(ts, torch.Tensor) else None
         if ts_list is not None and len(ts_list) and isinstance(ts_list[0], (np.integer, int)) and \
                 all(v is not None for v in ts_list):

@@ -1,0 +1,294 @@
+"""PyTorch loaders over a Reader (API of petastorm/pytorch.py: ``DataLoader`` :131-256, ``BatchedDataLoader`` :259-370,
+``InMemBatchedDataLoader`` :437-501, ``decimal_friendly_collate`` :73-95, ``_sanitize_pytorch_types`` :40-70).
+
+With a petastorm_b200 reader the rows are already device tensors, so the loaders differ from upstream in *where* data
+lives, not in what they yield:
+
+* :class:`DataLoader` keeps the row-at-a-time contract (``collate_fn`` over a list of row dicts, optional
+  ``RandomShufflingBuffer``); ``torch.stack`` then runs on the device.
+* :class:`BatchedDataLoader` is the fast path: whole decoded row-groups go into a device-resident batched shuffling
+  buffer (row gather kernel) and come out as ``{field: tensor[batch_size, ...]}``.
+* :class:`InMemBatchedDataLoader` decodes once into HBM and reshuffles per epoch with ``torch.Generator(seed+epoch)``.
+"""
+import collections.abc
+import decimal
+import logging
+import re
+
+import numpy as np
+import torch
+from torch.utils.data.dataloader import default_collate
+
+from petastorm_b200.reader_impl.pytorch_shuffling_buffer import (BatchedNoopShufflingBuffer,
+                                                                 BatchedRandomShufflingBuffer)
+from petastorm_b200.reader_impl.shuffling_buffer import NoopShufflingBuffer, RandomShufflingBuffer
+
+logger = logging.getLogger(__name__)
+_string_classes = (str, bytes)
+
+_TORCH_PROMOTIONS = {torch.uint16: torch.int32, torch.uint32: torch.int64, torch.bool: torch.uint8}
+
+
+def _sanitize_pytorch_types(row_as_dict):
+    """In-place dtype promotions PyTorch needs: uint16->int32, uint32->int64, bool->uint8; string/object arrays and
+    ``None`` are errors (petastorm/pytorch.py:40-70).  CUDA tensors are promoted by the K16 kernel."""
+    for name, value in row_as_dict.items():
+        if isinstance(value, torch.Tensor):
+            if value.dtype in _TORCH_PROMOTIONS:
+                if value.is_cuda:
+                    from petastorm_b200 import device_ops
+                    row_as_dict[name] = device_ops.sanitize(value)
+                else:
+                    row_as_dict[name] = value.to(_TORCH_PROMOTIONS[value.dtype])
+        elif isinstance(value, np.ndarray):
+            if value.dtype == np.uint16:
+                row_as_dict[name] = value.astype(np.int32)
+            elif value.dtype == np.uint32:
+                row_as_dict[name] = value.astype(np.int64)
+            elif value.dtype == np.bool_:
+                row_as_dict[name] = value.astype(np.uint8)
+            elif re.search('[SaUO]', value.dtype.str):
+                raise TypeError('Pytorch does not support arrays of string or object classes. '
+                                'Found in field {}.'.format(name))
+        elif isinstance(value, np.bool_):
+            row_as_dict[name] = np.uint8(value)
+        elif value is None:
+            raise TypeError('Pytorch does not support nullable fields. Found None in {}'.format(name))
+        elif isinstance(value, list) and any(v is None for v in value):
+            raise TypeError('Pytorch does not support nullable fields. Found None in {}'.format(name))
+
+
+def decimal_friendly_collate(batch):
+    """``default_collate`` that passes ``decimal.Decimal`` and strings through as lists (petastorm/pytorch.py:73-95)."""
+    first = batch[0]
+    if isinstance(first, decimal.Decimal):
+        return batch
+    if isinstance(first, collections.abc.Mapping):
+        return {key: decimal_friendly_collate([d[key] for d in batch]) for key in first}
+    if isinstance(first, _string_classes):
+        return batch
+    if isinstance(first, collections.abc.Sequence):
+        return [decimal_friendly_collate(samples) for samples in zip(*batch)]
+    return default_collate(batch)
+
+
+_PARALLEL_ITER_ERROR = "You must finish a full pass of Petastorm DataLoader before making another pass from the \
+beginning.If you do need to terminate early and restart from beginning, please re-create the reader and the data \
+loader."
+
+
+class LoaderBase(object):
+    """Re-iteration rules of petastorm/pytorch.py:103-128: a second pass resets the reader, a concurrent pass or a pass
+    after a failed one raises."""
+
+    def __init__(self):
+        self._in_iter = None
+        self._error = None
+
+    def __iter__(self):
+        if self._error is not None:
+            raise RuntimeError('Cannot start a new iteration because last time iteration failed with error {err}.'
+                               .format(err=repr(self._error)))
+        if self._in_iter is not None and self._in_iter == True:  # noqa: E712
+            raise RuntimeError(_PARALLEL_ITER_ERROR)
+        if self._in_iter is not None:
+            self.reader.reset()
+            logger.warning('Start a new pass of Petastorm DataLoader, reset underlying Petastorm reader to position 0.')
+        self._in_iter = True
+        try:
+            for batch in self._iter_impl():
+                yield batch
+        except Exception as e:
+            self._error = e
+            logger.error('Iteration on Petastorm DataLoader raise error: %s', repr(e))
+            raise
+        finally:
+            self._in_iter = False
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, exc_type, exc_val, exc_tb):
+        self.reader.stop()
+        self.reader.join()
+
+
+class DataLoader(LoaderBase):
+    """Row-at-a-time loader: rows -> (optional RandomShufflingBuffer) -> ``collate_fn(list of row dicts)``."""
+
+    def __init__(self, reader, batch_size=1, collate_fn=decimal_friendly_collate, shuffling_queue_capacity=0):
+        super(DataLoader, self).__init__()
+        self.reader = reader
+        self.batch_size = batch_size
+        self.collate_fn = collate_fn
+        self._batch_acc = []
+        self.shuffling_queue_capacity = shuffling_queue_capacity
+        self._in_iter = None
+
+    def _iter_impl(self):
+        keys = None
+        if self.shuffling_queue_capacity > 0:
+            self._shuffling_buffer = RandomShufflingBuffer(self.shuffling_queue_capacity,
+                                                           min_after_retrieve=self.shuffling_queue_capacity - 1,
+                                                           extra_capacity=100000000)
+        else:
+            self._shuffling_buffer = NoopShufflingBuffer()
+        for row in self.reader:
+            row_as_dict = row._asdict()
+            keys = row_as_dict.keys()
+            _sanitize_pytorch_types(row_as_dict)
+            if not self.reader.batched_output:
+                self._shuffling_buffer.add_many([row_as_dict])
+            else:
+                # a batched reader hands out whole row-groups: transpose to per-row tuples (upstream :207-216)
+                self._shuffling_buffer.add_many(list(zip(*(row_as_dict[k] for k in keys))))
+            for batch in self._yield_batches(keys):
+                yield batch
+        self._shuffling_buffer.finish()
+        for batch in self._yield_batches(keys):
+            yield batch
+        if self._batch_acc:
+            yield self.collate_fn(self._batch_acc)
+            self._batch_acc = []
+
+    def _yield_batches(self, keys):
+        while self._shuffling_buffer.can_retrieve():
+            item = self._shuffling_buffer.retrieve()
+            if not isinstance(item, dict):
+                item = dict(zip(keys, item))
+            self._batch_acc.append(item)
+            if len(self._batch_acc) == self.batch_size:
+                yield self.collate_fn(self._batch_acc)
+                self._batch_acc = []
+
+
+def _as_batch_tensor(value, transform_fn, batched):
+    """Column value of a row / row-group -> tensor with a leading row dimension."""
+    if isinstance(value, torch.Tensor):
+        return value if batched else value.unsqueeze(0)
+    return transform_fn(value) if batched else transform_fn([value])
+
+
+class BatchedDataLoader(LoaderBase):
+    """Batched loader: tensors in, ``{field: tensor[batch, ...]}`` out, shuffling through a batched buffer."""
+
+    def __init__(self, reader, batch_size=1, transform_fn=None, shuffling_queue_capacity=0):
+        super(BatchedDataLoader, self).__init__()
+        self.reader = reader
+        self.batch_size = batch_size
+        self.transform_fn = transform_fn or torch.as_tensor
+        self._batch_acc = []
+        self.shuffling_queue_capacity = shuffling_queue_capacity
+        self._in_iter = None
+
+    def _row_groups(self):
+        """Whole decoded row-groups when the reader can hand them out (petastorm_b200 row reader fast path), else the
+        reader's own items."""
+        qr = getattr(self.reader, '_results_queue_reader', None)
+        take_group = getattr(qr, 'read_next_rowgroup', None)
+        if take_group is None or self.reader.batched_output or self.reader.ngram:
+            for row in self.reader:
+                yield row._asdict(), self.reader.batched_output
+            return
+        while True:
+            try:
+                cols = take_group(self.reader._workers_pool)  # pylint: disable=protected-access
+            except StopIteration:
+                self.reader.last_row_consumed = True
+                return
+            yield cols, True
+
+    def _iter_impl(self):
+        keys = None
+        if self.shuffling_queue_capacity > 0:
+            min_after = self.shuffling_queue_capacity - 1
+            self._shuffling_buffer = BatchedRandomShufflingBuffer(min_after + self.batch_size,
+                                                                  min_after_retrieve=min_after,
+                                                                  extra_capacity=100000000,
+                                                                  batch_size=self.batch_size)
+        else:
+            self._shuffling_buffer = BatchedNoopShufflingBuffer(batch_size=self.batch_size)
+        for row_as_dict, batched in self._row_groups():
+            keys = row_as_dict.keys()
+            _sanitize_pytorch_types(row_as_dict)
+            for k, v in row_as_dict.items():
+                row_as_dict[k] = _as_batch_tensor(v, self.transform_fn, batched)
+            self._shuffling_buffer.add_many(row_as_dict.values())
+            for batch in self._yield_batches(keys):
+                yield batch
+        self._shuffling_buffer.finish()
+        for batch in self._yield_batches(keys):
+            yield batch
+
+    def _yield_batches(self, keys):
+        while self._shuffling_buffer.can_retrieve():
+            batch = self._shuffling_buffer.retrieve()
+            if not isinstance(batch, dict):
+                batch = dict(zip(keys, batch))
+            yield batch
+
+
+def _load_rows_into_mem(reader, transform_fn, rows_capacity):
+    """Up to ``rows_capacity`` rows into pre-allocated tensors, then stop the reader (petastorm/pytorch.py:373-434)."""
+    n_rows = 0
+    buffer = None
+    keys = None
+    for row in reader:
+        row_as_dict = row._asdict()
+        _sanitize_pytorch_types(row_as_dict)
+        for k, v in row_as_dict.items():
+            row_as_dict[k] = _as_batch_tensor(v, transform_fn, reader.batched_output)
+        if not keys:
+            keys = row_as_dict.keys()
+        items = list(row_as_dict.values())
+        take = min(len(items[0]), rows_capacity - n_rows)
+        if buffer is None:
+            buffer = [torch.empty((rows_capacity,) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device) for v in items]
+        for i, v in enumerate(items):
+            buffer[i][n_rows:n_rows + take] = v[:take]
+        n_rows += take
+        if n_rows >= rows_capacity:
+            break
+    reader.stop()
+    reader.join()
+    if buffer is not None and n_rows < rows_capacity:
+        buffer = [b[:n_rows] for b in buffer]
+    return keys, buffer
+
+
+class InMemBatchedDataLoader(object):
+    """Loads up to ``rows_capacity`` rows once (into HBM with a petastorm_b200 reader) and serves ``num_epochs``
+    epochs, reshuffled per epoch with ``torch.Generator().manual_seed(seed + epoch)`` like upstream (:469-493)."""
+
+    def __init__(self, reader, batch_size=1, transform_fn=None, num_epochs=1, seed=0, rows_capacity=1024,
+                 shuffle=False):
+        self._batch_size = batch_size
+        self._num_epochs = num_epochs
+        self._seed = seed
+        self._shuffle = shuffle
+        self._in_iter = False
+        self._keys, self._buffer = _load_rows_into_mem(reader, transform_fn or torch.as_tensor, rows_capacity)
+
+    def __iter__(self):
+        if self._in_iter:
+            raise RuntimeError("InMemBatchedDataLoader couldn't be used multiple times, please\
+                    specify total number of epochs using num_epochs in constructor.")
+        self._in_iter = True
+        from petastorm_b200.reader_impl.pytorch_shuffling_buffer import _take
+        size = len(self._buffer[0])
+        for epoch in range(self._num_epochs):
+            if self._shuffle:
+                g = torch.Generator()
+                g.manual_seed(self._seed + epoch)
+                indices = torch.randperm(size, generator=g)
+            else:
+                indices = torch.arange(size)
+            for i in range(0, size, self._batch_size):
+                idx = indices[i:i + self._batch_size].to(self._buffer[0].device)
+                yield dict(zip(self._keys, [_take(v, idx) for v in self._buffer]))
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, exc_type, exc_val, exc_tb):
+        pass
