@@ -237,11 +237,12 @@ def main():
         arenas.append(dec.upload(p))
     torch.cuda.synchronize()
     payload = sum(p.info.payload_bytes for p in plans) / len(plans)   # encoded bytes E per row-group
-    stream = dec.stream
+    stream = dec.streams[0]
 
     def resident_step(k):
         j = k % len(plans)
-        d = dec.decode_resident(plans[j], arenas[j], stream)
+        # consecutive row-groups on different streams, exactly like the readers (RowGroupDecoder.decode)
+        d = dec.decode_resident(plans[j], arenas[j], dec.streams[k % len(dec.streams)])
         col = d.column(0).values
         # consumer side: 4096-row batches are views of the row-group tensors (no copy)
         nb = (col.numel() + BATCH - 1) // BATCH
@@ -257,9 +258,15 @@ def main():
     keep = []
     barrier()
     e0.record(stream)
+    for other in dec.streams[1:]:
+        other.wait_event(e0)                     # every decode stream starts after the start event
+    last = {}
     for k in range(args.steps):
         d, _ = resident_step(args.warmup + k)
         keep = [d]
+        last[(args.warmup + k) % len(dec.streams)] = d.event
+    for ev in last.values():
+        stream.wait_event(ev)                    # the stop event waits for the last row-group of every stream
     e1.record(stream)
     barrier()
     dev_ms = e0.elapsed_time(e1)

@@ -105,22 +105,47 @@ __device__ __forceinline__ void coop_fill(uint8_t *dst, uint8_t v, int64_t n, in
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K2  Snappy.  One CTA of 4 warps per page.  Every warp walks the tag stream redundantly (uniform control flow, no
-// broadcast needed); literals >= kBigLiteral bytes are split across the 4 warps, everything else is executed by
-// warp 0.  A __syncthreads() after each big literal orders the other warps' stores before warp 0's later
-// back-references; __syncwarp() orders warp 0's own element-by-element dependencies.
+// K2  Snappy (raw block format, google/snappy format_description.txt).  One warp per page, uniform control flow.
+//
+// The element stream is a serial chain (every tag position depends on the previous element), and the streams that
+// matter here are made of tiny elements (C2 int64 pages: ~4.5-byte literals alternating with 4-byte copies, 2.3e5
+// elements in a 1 MiB dictionary page).  What makes such a chain slow on a GPU is the latency of each element's
+// loads, so both ends of the chain are kept in shared memory:
+//   * input  : the compressed bytes are staged by cp.async (LDGSTS) in a double-buffered 2 x 2 KiB window, the next
+//              chunk is in flight while the current one is parsed;
+//   * output : the most recent 32 KiB of output live in a shared-memory ring, so back-references (Snappy offsets are
+//              short for these streams) are LDS -> STS instead of a global store -> L2 -> global load round trip; the
+//              ring is written through to HBM in >= 4 KiB pieces with destination-aligned 16-byte stores.
+// Literals >= 1 KiB bypass both (vectorised global -> global copy); a back-reference that reaches outside the ring
+// (or into a bypassed literal) flushes the ring and reads the already written output from global memory.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kSnappyThreads = 128;
-constexpr int kBigLiteral = 2048;
+constexpr int kSnappyThreads = 32;
+constexpr int kRing = 32768;          // power of two
+constexpr int kRingMask = kRing - 1;
+constexpr int kFlushBytes = 4096;
+constexpr int kInChunk = 2048;        // power of two
+constexpr int kInMask = 2 * kInChunk - 1;
+constexpr int kBigLiteral = 1024;     // < kInChunk so that a staged literal never spans more than two chunks
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 __global__ void __launch_bounds__(kSnappyThreads)
 k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, const int32_t *__restrict__ list,
                int n_list, int32_t *status) {
+    // one allocation: the vector copies may read up to 15 bytes past the end of the ring (into the padding)
+    __shared__ __align__(16) uint8_t smem_all[kRing + 16 + 2 * kInChunk];
+    uint8_t *const ring = smem_all;
+    uint8_t *const inbuf = smem_all + kRing + 16;
     int li = blockIdx.x;
     if (li >= n_list) return;
-    int pi = list[li];
+    const int pi = list[li];
     const DevPage pg = pages[pi];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x;
 
     const uint8_t *src = arena + pg.src_off;
     uint8_t *dst = arena + pg.img_off;
@@ -130,91 +155,154 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
     // V2 data pages: the level bytes are stored uncompressed in front of the compressed values
     if (pg.kind == PK_DATA_V2) {
         int64_t lv = (int64_t)pg.def_bytes + pg.rep_bytes;
-        coop_copy(dst, src, lv, threadIdx.x, kSnappyThreads);
+        coop_copy(dst, src, lv, lane, kSnappyThreads);
         src += lv; dst += lv; src_n -= lv; dst_n -= lv;
-        __syncthreads();
+        __syncwarp();
         if (src_n <= 0) return;
     }
+#define SNAPPY_FAIL(code) do { if (lane == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, code); return; } while (0)
 
-    int64_t ip = 0;
-    // preamble: varint uncompressed length
+    // input addressing: `gin` is the 16-byte aligned base, `ip` / `in_end` are offsets from it
+    const uint8_t *gin = src - ((uintptr_t)src & 15);
+    int64_t ip = (int64_t)((uintptr_t)src & 15);
+    const int64_t in_end = ip + src_n;
+    const int64_t in_end16 = (in_end + 15) & ~(int64_t)15;
+
+    // preamble: varint uncompressed length (read straight from global: a handful of bytes)
     uint64_t ulen = 0;
     {
         int shift = 0;
         for (;;) {
-            if (ip >= src_n || shift > 35) { if (threadIdx.x == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, 1); return; }
-            uint8_t b = src[ip++];
+            if (ip >= in_end || shift > 35) SNAPPY_FAIL(1);
+            uint8_t b = gin[ip++];
             ulen |= (uint64_t)(b & 0x7f) << shift;
             if (!(b & 0x80)) break;
             shift += 7;
         }
     }
-    if ((int64_t)ulen != dst_n) { if (threadIdx.x == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, 2); return; }
+    if ((int64_t)ulen != dst_n) SNAPPY_FAIL(2);
 
-    int64_t op = 0;
-    while (ip < src_n) {
-        uint32_t tag = src[ip++];
-        uint32_t kind = tag & 3;
+    int64_t issued = (ip >> 11) - 1;    // last input chunk requested (kInChunk == 1 << 11)
+    int64_t arrived = issued;           // last input chunk known to be resident
+    int64_t op = 0;                     // output position
+    int64_t flushed = 0;                // output bytes already written to global memory
+    int64_t ring_valid_from = 0;        // output positions below this are not in the ring (bypassed literal)
+
+    auto issue_chunk = [&](int64_t c) {
+        const int64_t base = c << 11;
+        uint8_t *sdst = inbuf + ((c & 1) << 11);
+#pragma unroll
+        for (int k = 0; k < kInChunk / 16 / 32; k++) {
+            int64_t o = (int64_t)(lane + 32 * k) * 16;
+            if (base + o < in_end16) cp_async16(sdst + o, gin + base + o);
+        }
+        cp_async_commit();
+    };
+    // make input bytes [.., e) readable from inbuf
+    auto ensure_input = [&](int64_t e) {
+        const int64_t need = (e - 1) >> 11;
+        while (issued < need) { ++issued; issue_chunk(issued); }
+        if (arrived < need) {
+            cp_async_wait_all();
+            __syncwarp();
+            arrived = issued;
+        }
+    };
+    auto flush_to = [&](int64_t t) {
+        while (flushed < t) {
+            int64_t r = flushed & kRingMask;
+            int64_t n = min(t - flushed, (int64_t)kRing - r);
+            coop_copy(dst + flushed, ring + r, n, lane, kSnappyThreads);
+            flushed += n;
+        }
+    };
+#define IN(p) inbuf[(p) & kInMask]
+
+    while (ip < in_end) {
+        // keep one chunk of input in flight ahead of the parse position
+        {
+            const int64_t c = ip >> 11;
+            if (issued < c + 1 && ((c + 1) << 11) < in_end16) { ++issued; issue_chunk(issued); }
+        }
+        ensure_input(min(ip + 5, in_end));
+        const uint32_t tag = IN(ip);
+        ip++;
+        const uint32_t kind = tag & 3;
         if (kind == 0) {
             int64_t len = (tag >> 2) + 1;
             if (len > 60) {
-                int nb = (int)len - 60;
-                if (ip + nb > src_n) { if (threadIdx.x == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, 3); return; }
+                const int nb = (int)len - 60;
+                if (ip + nb > in_end) SNAPPY_FAIL(3);
                 uint32_t v = 0;
-                for (int i = 0; i < nb; i++) v |= (uint32_t)src[ip + i] << (8 * i);
+                for (int i = 0; i < nb; i++) v |= (uint32_t)IN(ip + i) << (8 * i);
                 len = (int64_t)v + 1;
                 ip += nb;
             }
-            if (ip + len > src_n || op + len > dst_n) { if (threadIdx.x == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, 4); return; }
+            if (ip + len > in_end || op + len > dst_n) SNAPPY_FAIL(4);
             if (len >= kBigLiteral) {
-                // split in 4 parts on 16-byte boundaries of the destination
-                int64_t part = ((len >> 2) + 15) & ~(int64_t)15;
-                int64_t b0 = (int64_t)warp * part;
-                int64_t b1 = b0 + part;
-                if (b1 > len || warp == 3) b1 = len;
-                if (b0 < len) coop_copy(dst + op + b0, src + ip + b0, b1 - b0, lane, 32);
-                __syncthreads();
-            } else if (warp == 0) {
-                coop_copy(dst + op, src + ip, len, lane, 32);
+                // bypass: ring -> global for what is pending, then one vectorised global -> global copy
+                flush_to(op);
+                coop_copy(dst + op, gin + ip, len, lane, kSnappyThreads);
+                ip += len;
+                op += len;
+                flushed = op;
+                ring_valid_from = op;
+                cp_async_wait_all();
                 __syncwarp();
+                issued = arrived = (ip >> 11) - 1;   // restart the staging window at the new position
+            } else {
+                ensure_input(ip + len);
+                for (int64_t i = lane; i < len; i += 32) ring[(op + i) & kRingMask] = IN(ip + i);
+                ip += len;
+                op += len;
             }
-            ip += len;
-            op += len;
         } else {
             uint32_t len, offset;
             if (kind == 1) {
-                if (ip >= src_n) { if (threadIdx.x == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, 5); return; }
+                if (ip >= in_end) SNAPPY_FAIL(5);
                 len = ((tag >> 2) & 7) + 4;
-                offset = ((tag >> 5) << 8) | src[ip];
+                offset = ((tag >> 5) << 8) | IN(ip);
                 ip += 1;
             } else if (kind == 2) {
-                if (ip + 2 > src_n) { if (threadIdx.x == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, 6); return; }
+                if (ip + 2 > in_end) SNAPPY_FAIL(6);
                 len = (tag >> 2) + 1;
-                offset = (uint32_t)src[ip] | ((uint32_t)src[ip + 1] << 8);
+                offset = (uint32_t)IN(ip) | ((uint32_t)IN(ip + 1) << 8);
                 ip += 2;
             } else {
-                if (ip + 4 > src_n) { if (threadIdx.x == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, 7); return; }
+                if (ip + 4 > in_end) SNAPPY_FAIL(7);
                 len = (tag >> 2) + 1;
-                offset = ld_u32_unaligned(src + ip);
+                offset = (uint32_t)IN(ip) | ((uint32_t)IN(ip + 1) << 8) | ((uint32_t)IN(ip + 2) << 16) |
+                         ((uint32_t)IN(ip + 3) << 24);
                 ip += 4;
             }
-            if (offset == 0 || (int64_t)offset > op || op + len > dst_n) {
-                if (threadIdx.x == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, 8);
-                return;
-            }
-            if (warp == 0) {
-                // len <= 64: at most two bytes per lane; the pattern form reads only bytes written by earlier elements
-                const uint8_t *from = dst + op - offset;
+            if (offset == 0 || (int64_t)offset > op || op + len > dst_n) SNAPPY_FAIL(8);
+            const int64_t sp = op - offset;
+            // len <= 64: at most two bytes per lane; the pattern form reads only bytes written by earlier elements
+            if (sp >= ring_valid_from && sp >= op + (int64_t)len - kRing) {
                 for (uint32_t i = lane; i < len; i += 32) {
                     uint32_t j = (offset >= len) ? i : (i % offset);
-                    dst[op + i] = from[j];
+                    ring[(op + i) & kRingMask] = ring[(sp + j) & kRingMask];
                 }
+            } else {
+                flush_to(op);
                 __syncwarp();
+                for (uint32_t i = lane; i < len; i += 32) {
+                    uint32_t j = (offset >= len) ? i : (i % offset);
+                    ring[(op + i) & kRingMask] = dst[sp + j];
+                }
             }
             op += len;
         }
+        __syncwarp();
+        if (op - flushed >= kFlushBytes) {
+            flush_to(op);
+            __syncwarp();
+        }
     }
-    if (op != dst_n && threadIdx.x == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, 9);
+    if (op != dst_n) SNAPPY_FAIL(9);
+    flush_to(op);
+#undef IN
+#undef SNAPPY_FAIL
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -142,6 +142,10 @@ class _GpuWorkerBase(WorkerBase):
         pvals = {k: v for k, v in piece.partition_keys if k in field_names}
         return _RawRowGroup(piece, decoded, pfile.schema, name_to_slot, pvals, num_rows)
 
+    def _stream_of(self, raw):
+        """The side stream that decoded `raw` (post-processing is queued behind the decode on the same stream)."""
+        return raw.decoded.stream if raw.decoded is not None else self._get_decoder().stream
+
     # ---- row selection ------------------------------------------------------------------------------------------
     def _row_order(self, num_rows, shuffle_row_drop_partition, ngram_length=0):
         """Host int64 array of source rows in output order, or None for "all rows, natural order".
@@ -420,7 +424,7 @@ class GpuArrowWorker(_GpuWorkerBase):
         names = [f.name for f in self._schema.fields.values()]
         raw = self._read_raw(piece, names)
         order = self._row_order(raw.num_rows, shuffle_row_drop_partition)
-        with torch.cuda.stream(self._get_decoder().stream):
+        with torch.cuda.stream(self._stream_of(raw)):
             cols = self._build_columns(raw, names, order)
             count = raw.num_rows if order is None else len(order)
             if self._transform_spec:
@@ -451,7 +455,7 @@ class GpuArrowWorker(_GpuWorkerBase):
         # 1. predicate columns first
         raw_p = self._read_raw(piece, predicate_fields)
         order = self._row_order(raw_p.num_rows, shuffle_row_drop_partition)
-        with torch.cuda.stream(decoder.stream):
+        with torch.cuda.stream(self._stream_of(raw_p)):
             pcols = self._build_columns(raw_p, sorted(predicate_fields), order)
             mask = worker_predicate.device_mask(pcols)
             if mask is None:
@@ -861,8 +865,7 @@ class GpuPyDictWorker(_GpuWorkerBase):
         raw = self._read_raw(piece, names)
         order = self._row_order(raw.num_rows, shuffle_row_drop_partition,
                                 self._ngram.length if self._ngram else 0)
-        decoder = self._get_decoder()
-        with torch.cuda.stream(decoder.stream):
+        with torch.cuda.stream(self._stream_of(raw)):
             cols = self._decode_all(raw, names, order)
             count = raw.num_rows if order is None else len(order)
             if self._transform_spec:
@@ -896,7 +899,7 @@ class GpuPyDictWorker(_GpuWorkerBase):
         raw_p = self._read_raw(piece, predicate_fields)
         order = self._row_order(raw_p.num_rows, shuffle_row_drop_partition,
                                 self._ngram.length if self._ngram else 0)
-        with torch.cuda.stream(decoder.stream):
+        with torch.cuda.stream(self._stream_of(raw_p)):
             pcols = self._decode_all(raw_p, sorted(predicate_fields), order)
             count = raw_p.num_rows if order is None else len(order)
             mask = self._predicate_mask(worker_predicate, raw_p, pcols, order, count)

@@ -156,24 +156,37 @@ class DecodedRowGroup(object):
 
 
 class RowGroupDecoder(object):
-    """Issues plan -> upload -> decode for row-groups on a side stream of one device."""
+    """Issues plan -> upload -> decode for row-groups on side streams of one device."""
+
+    NUM_STREAMS = 3
 
     def __init__(self, device=None):
         self.ctx = get_context(device)
         self.device = torch.device('cuda', self.ctx.device)
-        self.stream = torch.cuda.Stream(self.device)
+        # consecutive row-groups go to different streams so that the serial tail of one row-group's decode (a few long
+        # Snappy streams) overlaps with the bulk of the next one
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(self.NUM_STREAMS)]
+        self._next_stream = 0
+        self.stream = self.streams[0]
         self.launches = 0
         self.h2d_bytes = 0
 
     def plan(self, path, row_group, leaf_columns):
         return native.Plan(open_file(path), row_group, leaf_columns)
 
-    def upload(self, plan):
-        """H2D of a plan's raw region into a fresh arena; returns the arena tensor (async on self.stream)."""
-        with torch.cuda.stream(self.stream):
+    def next_stream(self):
+        s = self.streams[self._next_stream]
+        self._next_stream = (self._next_stream + 1) % len(self.streams)
+        self.stream = s
+        return s
+
+    def upload(self, plan, stream=None):
+        """H2D of a plan's raw region into a fresh arena; returns the arena tensor (async on `stream`)."""
+        stream = stream or self.stream
+        with torch.cuda.stream(stream):
             arena = torch.empty(plan.info.arena_bytes, dtype=torch.uint8, device=self.device)
         native.check(native.lib.pst_plan_upload(self.ctx.handle, plan.handle, arena.data_ptr(),
-                                                self.stream.cuda_stream), 'pst_plan_upload')
+                                                stream.cuda_stream), 'pst_plan_upload')
         self.h2d_bytes += plan.info.raw_bytes
         return arena
 
@@ -191,8 +204,9 @@ class RowGroupDecoder(object):
 
     def decode(self, path, row_group, leaf_columns):
         plan = self.plan(path, row_group, leaf_columns)
-        arena = self.upload(plan)
-        return self.decode_resident(plan, arena)
+        stream = self.next_stream()
+        arena = self.upload(plan, stream)
+        return self.decode_resident(plan, arena, stream)
 
 
 def gather_blobs_to_host(col, row_indices=None):
