@@ -105,27 +105,52 @@ __device__ __forceinline__ void coop_fill(uint8_t *dst, uint8_t v, int64_t n, in
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K2  Snappy (raw block format, google/snappy format_description.txt).  One warp per page, uniform control flow.
+// K2  Snappy (raw block format, google/snappy format_description.txt).  One CTA = one page = two warps:
 //
-// The element stream is a serial chain (every tag position depends on the previous element), and the streams that
-// matter here are made of tiny elements (C2 int64 pages: ~4.5-byte literals alternating with 4-byte copies, 2.3e5
-// elements in a 1 MiB dictionary page).  What makes such a chain slow on a GPU is the latency of each element's
-// loads, so both ends of the chain are kept in shared memory:
-//   * input  : the compressed bytes are staged by cp.async (LDGSTS) in a double-buffered 2 x 2 KiB window, the next
-//              chunk is in flight while the current one is parsed;
-//   * output : the most recent 32 KiB of output live in a shared-memory ring, so back-references (Snappy offsets are
-//              short for these streams) are LDS -> STS instead of a global store -> L2 -> global load round trip; the
-//              ring is written through to HBM in >= 4 KiB pieces with destination-aligned 16-byte stores.
-// Literals >= 1 KiB bypass both (vectorised global -> global copy); a back-reference that reaches outside the ring
-// (or into a bypassed literal) flushes the ring and reads the already written output from global memory.
+//   warp P (parser)    walks the element stream -- an inherently serial chain, every tag position depends on the
+//                      previous element -- with as few instructions per element as possible: tag bytes come from a
+//                      shared-memory staging window filled by cp.async (LDGSTS), and the only output is one 8-byte
+//                      record {source/offset, length|kind} per element, written to a double-buffered batch in shared
+//                      memory (<= 32 elements, <= 1 KiB of input, <= 4 KiB of output per batch).
+//   warp X (executor)  takes one element per lane: a warp scan of the lengths gives every element its output
+//                      position, literal bytes go staging -> ring, back-references ring -> ring in dependency rounds
+//                      (a copy runs once every element in front of its source range is complete).  The ring holds the
+//                      most recent 32 KiB of output in shared memory, so the many tiny copies of a match-heavy stream
+//                      never pay a global store -> L2 -> global load round trip; it is written through to HBM in
+//                      >= 4 KiB pieces with destination-aligned 16-byte stores.
+//
+// The two warps hand batches over with named barriers (bar.arrive / bar.sync), so P parses batch b+1 while X executes
+// batch b.  Literals >= 1 KiB bypass staging and ring (one vectorised global -> global copy by X).  A back-reference
+// that reaches outside the ring, or into a bypassed literal, is served from the output already written to HBM.
+//
+// Why this shape: measured on B200 (profiles/r1_snappy_v2_ring.txt) a lone warp retires ~1 dependent instruction per
+// ~5 cycles, so the cost of a page is (instructions on the serial chain) x 5 cycles x elements; the 1 MiB dictionary
+// page of a C2 int64 column has 2.3e5 elements and sets the latency of the whole row-group.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kSnappyThreads = 32;
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane);   // defined with the page decoder below
+
+constexpr int kSnappyThreads = 64;
 constexpr int kRing = 32768;          // power of two
-constexpr int kRingMask = kRing - 1;
-constexpr int kFlushBytes = 4096;
-constexpr int kInChunk = 2048;        // power of two
-constexpr int kInMask = 2 * kInChunk - 1;
-constexpr int kBigLiteral = 1024;     // < kInChunk so that a staged literal never spans more than two chunks
+constexpr uint32_t kRingMask = kRing - 1;
+constexpr int kStage = 8192;          // input staging window: 4 chunks of 2 KiB (power of two)
+constexpr uint32_t kStageMask = kStage - 1;
+constexpr int kChunkShift = 11;
+constexpr uint32_t kChunk = 1u << kChunkShift;
+constexpr int kBatchOps = 32;
+constexpr uint32_t kBatchIn = 1024;   // a batch is closed after this many input bytes ...
+constexpr uint32_t kBatchOut = 4096;  // ... or this many output bytes
+constexpr uint32_t kBigLiteral = 1024;
+constexpr uint32_t kFlushBytes = 4096;
+constexpr uint32_t kLookahead = kBatchIn + kBigLiteral + 8;   // staged bytes a batch may touch past its start
+
+struct SnBatch {
+    uint2 rec[kBatchOps];   // .x = literal: input offset of the bytes | copy: back-reference offset
+                            // .y = length | kind << 24   (kind 0 literal, 1 copy, 2 bypassed big literal)
+    uint32_t n;
+    uint32_t last;          // no batch follows
+    uint32_t err;           // parser error code (0 = ok)
+    uint32_t big_len;       // length of the kind-2 element (always the last of its batch)
+};
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
@@ -133,176 +158,294 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(count) : "memory");
+}
+constexpr int kBarFull = 1;    // +slot : P arrives, X syncs
+constexpr int kBarEmpty = 3;   // +slot : X arrives, P syncs
 
 __global__ void __launch_bounds__(kSnappyThreads)
 k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, const int32_t *__restrict__ list,
                int n_list, int32_t *status) {
     // one allocation: the vector copies may read up to 15 bytes past the end of the ring (into the padding)
-    __shared__ __align__(16) uint8_t smem_all[kRing + 16 + 2 * kInChunk];
+    __shared__ __align__(16) uint8_t smem_all[kRing + 16 + kStage];
+    __shared__ __align__(16) SnBatch batches[2];
+    __shared__ volatile uint32_t abort_flag;
     uint8_t *const ring = smem_all;
-    uint8_t *const inbuf = smem_all + kRing + 16;
-    int li = blockIdx.x;
+    uint8_t *const stage = smem_all + kRing + 16;
+    const int li = blockIdx.x;
     if (li >= n_list) return;
     const int pi = list[li];
     const DevPage pg = pages[pi];
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool is_parser = threadIdx.x < 32;
 
     const uint8_t *src = arena + pg.src_off;
     uint8_t *dst = arena + pg.img_off;
-    int64_t src_n = pg.comp_size;
-    int64_t dst_n = pg.uncomp_size;
+    uint32_t src_n = (uint32_t)pg.comp_size;
+    uint32_t dst_n = (uint32_t)pg.uncomp_size;
+    if (threadIdx.x == 0) abort_flag = 0;
 
     // V2 data pages: the level bytes are stored uncompressed in front of the compressed values
     if (pg.kind == PK_DATA_V2) {
-        int64_t lv = (int64_t)pg.def_bytes + pg.rep_bytes;
-        coop_copy(dst, src, lv, lane, kSnappyThreads);
+        uint32_t lv = (uint32_t)(pg.def_bytes + pg.rep_bytes);
+        if (!is_parser) coop_copy(dst, src, lv, lane, 32);
         src += lv; dst += lv; src_n -= lv; dst_n -= lv;
-        __syncwarp();
-        if (src_n <= 0) return;
     }
-#define SNAPPY_FAIL(code) do { if (lane == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, code); return; } while (0)
+    __syncthreads();
+    if ((int32_t)src_n <= 0) return;
 
-    // input addressing: `gin` is the 16-byte aligned base, `ip` / `in_end` are offsets from it
+    // input addressing: `gin` is the 16-byte aligned base, positions are 32-bit offsets from it
     const uint8_t *gin = src - ((uintptr_t)src & 15);
-    int64_t ip = (int64_t)((uintptr_t)src & 15);
-    const int64_t in_end = ip + src_n;
-    const int64_t in_end16 = (in_end + 15) & ~(int64_t)15;
+    const uint32_t in_begin = (uint32_t)((uintptr_t)src & 15);
+    const uint32_t in_end = in_begin + src_n;
+    const uint32_t in_end16 = (in_end + 15) & ~15u;
 
-    // preamble: varint uncompressed length (read straight from global: a handful of bytes)
-    uint64_t ulen = 0;
-    {
-        int shift = 0;
-        for (;;) {
-            if (ip >= in_end || shift > 35) SNAPPY_FAIL(1);
-            uint8_t b = gin[ip++];
-            ulen |= (uint64_t)(b & 0x7f) << shift;
-            if (!(b & 0x80)) break;
-            shift += 7;
-        }
-    }
-    if ((int64_t)ulen != dst_n) SNAPPY_FAIL(2);
-
-    int64_t issued = (ip >> 11) - 1;    // last input chunk requested (kInChunk == 1 << 11)
-    int64_t arrived = issued;           // last input chunk known to be resident
-    int64_t op = 0;                     // output position
-    int64_t flushed = 0;                // output bytes already written to global memory
-    int64_t ring_valid_from = 0;        // output positions below this are not in the ring (bypassed literal)
-
-    auto issue_chunk = [&](int64_t c) {
-        const int64_t base = c << 11;
-        uint8_t *sdst = inbuf + ((c & 1) << 11);
-#pragma unroll
-        for (int k = 0; k < kInChunk / 16 / 32; k++) {
-            int64_t o = (int64_t)(lane + 32 * k) * 16;
-            if (base + o < in_end16) cp_async16(sdst + o, gin + base + o);
-        }
-        cp_async_commit();
-    };
-    // make input bytes [.., e) readable from inbuf
-    auto ensure_input = [&](int64_t e) {
-        const int64_t need = (e - 1) >> 11;
-        while (issued < need) { ++issued; issue_chunk(issued); }
-        if (arrived < need) {
-            cp_async_wait_all();
-            __syncwarp();
-            arrived = issued;
-        }
-    };
-    auto flush_to = [&](int64_t t) {
-        while (flushed < t) {
-            int64_t r = flushed & kRingMask;
-            int64_t n = min(t - flushed, (int64_t)kRing - r);
-            coop_copy(dst + flushed, ring + r, n, lane, kSnappyThreads);
-            flushed += n;
-        }
-    };
-#define IN(p) inbuf[(p) & kInMask]
-
-    while (ip < in_end) {
-        // keep one chunk of input in flight ahead of the parse position
-        {
-            const int64_t c = ip >> 11;
-            if (issued < c + 1 && ((c + 1) << 11) < in_end16) { ++issued; issue_chunk(issued); }
-        }
-        ensure_input(min(ip + 5, in_end));
-        const uint32_t tag = IN(ip);
-        ip++;
-        const uint32_t kind = tag & 3;
-        if (kind == 0) {
-            int64_t len = (tag >> 2) + 1;
-            if (len > 60) {
-                const int nb = (int)len - 60;
-                if (ip + nb > in_end) SNAPPY_FAIL(3);
-                uint32_t v = 0;
-                for (int i = 0; i < nb; i++) v |= (uint32_t)IN(ip + i) << (8 * i);
-                len = (int64_t)v + 1;
-                ip += nb;
+    if (is_parser) {
+        // ============================================ warp P =====================================================
+        uint32_t ip = in_begin;
+        uint32_t first_err = 0;
+        {   // preamble: varint uncompressed length (a handful of bytes, read straight from global)
+            uint64_t ulen = 0;
+            int shift = 0;
+            for (;;) {
+                if (ip >= in_end || shift > 35) { first_err = 1; break; }
+                uint8_t b = gin[ip++];
+                ulen |= (uint64_t)(b & 0x7f) << shift;
+                if (!(b & 0x80)) break;
+                shift += 7;
             }
-            if (ip + len > in_end || op + len > dst_n) SNAPPY_FAIL(4);
-            if (len >= kBigLiteral) {
-                // bypass: ring -> global for what is pending, then one vectorised global -> global copy
-                flush_to(op);
-                coop_copy(dst + op, gin + ip, len, lane, kSnappyThreads);
-                ip += len;
-                op += len;
-                flushed = op;
-                ring_valid_from = op;
+            if (!first_err && ulen != (uint64_t)dst_n) first_err = 2;
+        }
+        uint32_t issued_end = ip & ~(kChunk - 1);   // input bytes below this have been requested
+        uint32_t ready_end = issued_end;            // input bytes below this are resident in `stage`
+        uint32_t keep_from = ip;                    // start of the previous batch: X may still read literals from there
+        uint32_t placed[2] = {0, 0}, consumed[2] = {0, 0};
+        bool restart = false;
+        for (uint32_t b = 0;; b++) {
+            const int s = b & 1;
+            while (consumed[s] < placed[s]) { named_bar_sync(kBarEmpty + s, 64); consumed[s]++; }
+            if (restart) {   // after a bypassed literal the staging window moves: wait until X is done with everything
+                while (consumed[s ^ 1] < placed[s ^ 1]) { named_bar_sync(kBarEmpty + (s ^ 1), 64); consumed[s ^ 1]++; }
+                issued_end = ready_end = ip & ~(kChunk - 1);
+                keep_from = ip;
+                restart = false;
+            }
+            SnBatch &bt = batches[s];
+            // lane 0 decides (the flag may flip while the lanes read it): keeps the warp's control flow uniform
+            const bool stop = __shfl_sync(0xffffffffu, (int)(abort_flag != 0 || first_err != 0), 0) != 0;
+            if (!stop && ip < in_end && ip + kLookahead > ready_end && ready_end < in_end16) {
+                // refill: every chunk that does not overwrite [keep_from, ...) ; 4 chunk slots
+                const uint32_t target = ((keep_from >> kChunkShift) + 4) << kChunkShift;
+                while (issued_end < target && issued_end < in_end16) {
+                    uint8_t *sdst = stage + (issued_end & kStageMask);
+#pragma unroll
+                    for (int k = 0; k < (int)kChunk / 16 / 32; k++) {
+                        uint32_t o = (uint32_t)(lane + 32 * k) * 16;
+                        if (issued_end + o < in_end16) cp_async16(sdst + o, gin + issued_end + o);
+                    }
+                    issued_end += kChunk;
+                }
+                cp_async_commit();
                 cp_async_wait_all();
                 __syncwarp();
-                issued = arrived = (ip >> 11) - 1;   // restart the staging window at the new position
-            } else {
-                ensure_input(ip + len);
-                for (int64_t i = lane; i < len; i += 32) ring[(op + i) & kRingMask] = IN(ip + i);
-                ip += len;
-                op += len;
+                ready_end = issued_end;
             }
-        } else {
-            uint32_t len, offset;
-            if (kind == 1) {
-                if (ip >= in_end) SNAPPY_FAIL(5);
-                len = ((tag >> 2) & 7) + 4;
-                offset = ((tag >> 5) << 8) | IN(ip);
-                ip += 1;
-            } else if (kind == 2) {
-                if (ip + 2 > in_end) SNAPPY_FAIL(6);
-                len = (tag >> 2) + 1;
-                offset = (uint32_t)IN(ip) | ((uint32_t)IN(ip + 1) << 8);
-                ip += 2;
-            } else {
-                if (ip + 4 > in_end) SNAPPY_FAIL(7);
-                len = (tag >> 2) + 1;
-                offset = (uint32_t)IN(ip) | ((uint32_t)IN(ip + 1) << 8) | ((uint32_t)IN(ip + 2) << 16) |
-                         ((uint32_t)IN(ip + 3) << 24);
-                ip += 4;
-            }
-            if (offset == 0 || (int64_t)offset > op || op + len > dst_n) SNAPPY_FAIL(8);
-            const int64_t sp = op - offset;
-            // len <= 64: at most two bytes per lane; the pattern form reads only bytes written by earlier elements
-            if (sp >= ring_valid_from && sp >= op + (int64_t)len - kRing) {
-                for (uint32_t i = lane; i < len; i += 32) {
-                    uint32_t j = (offset >= len) ? i : (i % offset);
-                    ring[(op + i) & kRingMask] = ring[(sp + j) & kRingMask];
+            uint32_t n = 0, err = first_err, big = 0, big_len = 0;
+            const uint32_t batch_start = ip;
+            if (lane == 0 && !stop) {
+                uint32_t out_acc = 0;
+                const uint32_t lim = min(ip + kBatchIn, in_end);
+#define IN(p) stage[(p) & kStageMask]
+                while (n < (uint32_t)kBatchOps && ip < lim && out_acc < kBatchOut) {
+                    const uint32_t tag = IN(ip);
+                    uint32_t lo, hi;
+                    if ((tag & 3) == 0) {
+                        uint32_t len = (tag >> 2) + 1;
+                        uint32_t p = ip + 1;
+                        if (len > 60) {
+                            const uint32_t nb = len - 60;
+                            uint32_t v = 0;
+                            for (uint32_t i = 0; i < nb; i++) v |= (uint32_t)IN(p + i) << (8 * i);
+                            len = v + 1;
+                            p += nb;
+                        }
+                        if (p > in_end || len > in_end - p || len > dst_n) { err = 4; break; }
+                        if (len >= kBigLiteral) {
+                            bt.rec[n++] = make_uint2(p, 2u << 24);
+                            big = 1;
+                            big_len = len;
+                            ip = p + len;
+                            break;
+                        }
+                        lo = p;
+                        hi = len;
+                        ip = p + len;
+                        out_acc += len;
+                    } else if ((tag & 3) == 1) {
+                        const uint32_t len = ((tag >> 2) & 7) + 4;
+                        lo = ((tag >> 5) << 8) | IN(ip + 1);
+                        hi = len | (1u << 24);
+                        ip += 2;
+                        out_acc += len;
+                    } else if ((tag & 3) == 2) {
+                        const uint32_t len = (tag >> 2) + 1;
+                        lo = (uint32_t)IN(ip + 1) | ((uint32_t)IN(ip + 2) << 8);
+                        hi = len | (1u << 24);
+                        ip += 3;
+                        out_acc += len;
+                    } else {
+                        const uint32_t len = (tag >> 2) + 1;
+                        lo = (uint32_t)IN(ip + 1) | ((uint32_t)IN(ip + 2) << 8) | ((uint32_t)IN(ip + 3) << 16) |
+                             ((uint32_t)IN(ip + 4) << 24);
+                        hi = len | (1u << 24);
+                        ip += 5;
+                        out_acc += len;
+                    }
+                    bt.rec[n++] = make_uint2(lo, hi);
                 }
-            } else {
-                flush_to(op);
-                __syncwarp();
-                for (uint32_t i = lane; i < len; i += 32) {
-                    uint32_t j = (offset >= len) ? i : (i % offset);
-                    ring[(op + i) & kRingMask] = dst[sp + j];
-                }
+#undef IN
+                if (!err && ip > in_end) err = 5;   // an element header ran past the end of the stream
             }
-            op += len;
-        }
-        __syncwarp();
-        if (op - flushed >= kFlushBytes) {
-            flush_to(op);
+            n = __shfl_sync(0xffffffffu, n, 0);
+            ip = __shfl_sync(0xffffffffu, ip, 0);
+            err = __shfl_sync(0xffffffffu, err, 0);
+            big = __shfl_sync(0xffffffffu, big, 0);
+            big_len = __shfl_sync(0xffffffffu, big_len, 0);
+            const bool last = stop || err != 0 || ip >= in_end;
+            if (lane == 0) {
+                bt.n = n;
+                bt.err = err;
+                bt.last = last ? 1u : 0u;
+                bt.big_len = big_len;
+            }
+            keep_from = batch_start;
+            if (big) restart = true;
             __syncwarp();
+            __threadfence_block();
+            placed[s]++;
+            named_bar_arrive(kBarFull + s, 64);
+            if (last) return;
+        }
+    } else {
+        // ============================================ warp X =====================================================
+        uint32_t dst0 = 0;            // output position of the next batch
+        uint32_t flushed = 0;         // output bytes already written to global memory
+        uint32_t valid_from = 0;      // output positions below this are not in the ring (bypassed literal)
+        bool failed = false;
+        auto flush_to = [&](uint32_t t) {
+            while (flushed < t) {
+                const uint32_t r = flushed & kRingMask;
+                const uint32_t nn = min(t - flushed, (uint32_t)kRing - r);
+                coop_copy(dst + flushed, ring + r, nn, lane, 32);
+                flushed += nn;
+            }
+        };
+        for (uint32_t b = 0;; b++) {
+            const int s = b & 1;
+            named_bar_sync(kBarFull + s, 64);
+            const SnBatch &bt = batches[s];
+            const uint32_t n = bt.n, last = bt.last, perr = bt.err, big_len = bt.big_len;
+            if (perr && !failed) {
+                failed = true;
+                if (lane == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, (int)perr);
+            }
+            if (!failed) {
+                const uint2 r = lane < (int)n ? bt.rec[lane] : make_uint2(0, 0);
+                const uint32_t kind = r.y >> 24;
+                const uint32_t a = r.x;
+                const uint32_t len = (lane < (int)n && kind != 2) ? (r.y & 0xffffffu) : 0u;
+                const uint32_t incl = warp_incl_scan(len, lane);
+                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                const uint32_t d = dst0 + incl - len;          // output position of this lane's element
+                const bool is_copy = lane < (int)n && kind == 1;
+                bool bad = (d + len > dst_n) || (is_copy && (a == 0 || a > d));
+                if (__any_sync(0xffffffffu, bad)) {
+                    failed = true;
+                    abort_flag = 1;
+                    if (lane == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, 8);
+                } else {
+                    // ---- literals: staging -> ring.  Short ones per lane, longer ones by the whole warp.
+                    const bool is_lit = lane < (int)n && kind == 0;
+                    if (is_lit && len <= 16) {
+                        for (uint32_t i = 0; i < len; i++) ring[(d + i) & kRingMask] = stage[(a + i) & kStageMask];
+                    }
+                    uint32_t longs = __ballot_sync(0xffffffffu, is_lit && len > 16);
+                    while (longs) {
+                        const int l = __ffs(longs) - 1;
+                        longs &= longs - 1;
+                        const uint32_t bl = __shfl_sync(0xffffffffu, len, l);
+                        const uint32_t bd = __shfl_sync(0xffffffffu, d, l);
+                        const uint32_t ba = __shfl_sync(0xffffffffu, a, l);
+                        for (uint32_t i = lane; i < bl; i += 32) ring[(bd + i) & kRingMask] = stage[(ba + i) & kStageMask];
+                    }
+                    __syncwarp();
+                    // ---- back-references in dependency rounds
+                    const uint32_t sp = d - a;                                   // source position (copies only)
+                    const uint32_t src_end = min(sp + len, d);                   // bytes >= d are produced by the lane itself
+                    const bool in_ring = sp >= valid_from && (dst0 + total) - sp <= (uint32_t)kRing;
+                    uint32_t pending = __ballot_sync(0xffffffffu, is_copy);
+                    while (pending) {
+                        const int first = __ffs(pending) - 1;
+                        const uint32_t done_pos = __shfl_sync(0xffffffffu, d, first);   // everything below is complete
+                        const bool mine = (pending >> lane) & 1;
+                        bool ready = mine && (lane == first || src_end <= done_pos);
+                        if (ready && !in_ring && lane != first) ready = false;       // far sources wait for their turn
+                        const bool far_first = __shfl_sync(0xffffffffu, (int)(ready && !in_ring), first) != 0;
+                        if (far_first) {
+                            // the source left the ring (or was bypassed): complete output below done_pos goes to HBM first
+                            flush_to(done_pos);
+                            __syncwarp();
+                            if (lane == first) {
+                                for (uint32_t i = 0; i < len; i++) {
+                                    const uint32_t q = sp + i;
+                                    ring[(d + i) & kRingMask] = q < done_pos ? dst[q] : ring[q & kRingMask];
+                                }
+                            }
+                        }
+                        if (ready && in_ring) {
+                            // sequential per lane: an overlapping copy (offset < length) re-reads its own bytes
+                            for (uint32_t i = 0; i < len; i++) ring[(d + i) & kRingMask] = ring[(d + i - a) & kRingMask];
+                        }
+                        pending &= ~__ballot_sync(0xffffffffu, ready);
+                        __syncwarp();
+                    }
+                    dst0 += total;
+                    // ---- bypassed big literal (always the last element of its batch)
+                    if (n > 0 && __shfl_sync(0xffffffffu, kind, (int)n - 1) == 2) {
+                        const uint32_t bsrc = __shfl_sync(0xffffffffu, a, (int)n - 1);
+                        if (dst0 + big_len > dst_n) {
+                            failed = true;
+                            abort_flag = 1;
+                            if (lane == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, 4);
+                        } else {
+                            flush_to(dst0);
+                            coop_copy(dst + dst0, gin + bsrc, big_len, lane, 32);
+                            dst0 += big_len;
+                            flushed = dst0;
+                            valid_from = dst0;
+                            __syncwarp();
+                        }
+                    }
+                    if (dst0 - flushed >= kFlushBytes) {
+                        flush_to(dst0);
+                        __syncwarp();
+                    }
+                }
+            }
+            if (last) {
+                if (!failed) {
+                    if (dst0 != dst_n) { if (lane == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, 9); }
+                    else flush_to(dst0);
+                }
+                return;
+            }
+            named_bar_arrive(kBarEmpty + s, 64);
         }
     }
-    if (op != dst_n) SNAPPY_FAIL(9);
-    flush_to(op);
-#undef IN
-#undef SNAPPY_FAIL
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -343,7 +486,7 @@ __global__ void k_ba_dict_index(uint8_t *__restrict__ arena, const DevPage *__re
 // the CTA expand table entries in parallel (bit extraction for bit-packed runs).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kDecThreads = 256;
-constexpr int kTile = 2048;       // values per tile
+constexpr int kTile = 1024;       // values per tile (4 x 256 threads); sizes the shared-memory staging (~32 KB per CTA)
 constexpr int kRunCap = 256;      // run-table entries per scan round
 
 struct HybridCursor {

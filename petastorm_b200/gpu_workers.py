@@ -126,8 +126,14 @@ class _GpuWorkerBase(WorkerBase):
         leaves = pfile.schema['leaves']
         wanted = [n for n in field_names if n not in partition_names]
         name_to_slot, leaf_ids = {}, []
+        by_name = getattr(pfile, '_leaves_by_name', None)
+        if by_name is None:
+            by_name = {}
+            for l in leaves:
+                by_name.setdefault(l['path'][0], []).append(l['index'])
+            pfile._leaves_by_name = by_name  # pylint: disable=protected-access
         for name in wanted:
-            ids = [l['index'] for l in leaves if l['path'][0] == name]
+            ids = by_name.get(name, [])
             if not ids:
                 raise ValueError('Field {} was not found in the file {}'.format(name, piece.path))
             if len(ids) > 1:
@@ -328,6 +334,8 @@ class GpuArrowResultsQueueReader(object):
         try:
             assert not ngram, 'ArrowReader does not support ngrams for now'
             batch = workers_pool.get_results()
+            if isinstance(batch, PendingRowGroup):
+                batch = batch.resolve()
             batch.wait()
             cols = batch.columns
             if self._output == 'numpy':
@@ -352,6 +360,12 @@ class GpuArrowWorker(_GpuWorkerBase):
         self._check_cache_usage(worker_predicate, shuffle_row_drop_partition)
         if worker_predicate:
             batch = self._load_rows_with_predicate(piece, worker_predicate, shuffle_row_drop_partition)
+        elif isinstance(self._local_cache, NullCache):
+            # asynchronous: issue the device work now, resolve on the consumer side
+            pending = self._issue_rows(piece, shuffle_row_drop_partition)
+            if pending.num_rows:
+                self.publish_func(pending)
+            return
         else:
             batch = self._local_cache.get(self._cache_key(piece, piece_index),
                                           lambda: self._load_rows(piece, shuffle_row_drop_partition))
@@ -420,18 +434,26 @@ class GpuArrowWorker(_GpuWorkerBase):
             out[name] = self._materialize(raw, name, self._schema.fields[name], order)
         return out
 
-    def _load_rows(self, piece, shuffle_row_drop_partition):
+    def _issue_rows(self, piece, shuffle_row_drop_partition):
         names = [f.name for f in self._schema.fields.values()]
-        raw = self._read_raw(piece, names)
-        order = self._row_order(raw.num_rows, shuffle_row_drop_partition)
-        with torch.cuda.stream(self._stream_of(raw)):
-            cols = self._build_columns(raw, names, order)
-            count = raw.num_rows if order is None else len(order)
-            if self._transform_spec:
-                cols = self._apply_transform(cols, count)
-            done = torch.cuda.Event()
-            done.record()
-        return GpuBatch(cols, count, [_EventWaiter(done), raw.decoded])
+        raw = self._read_raw(piece, names)                                  # plan + H2D + decode kernels, all async
+        order = self._row_order(raw.num_rows, shuffle_row_drop_partition)   # RNG drawn here: order of issue is fixed
+        count = raw.num_rows if order is None else len(order)
+
+        def finalize():
+            with torch.cuda.stream(self._stream_of(raw)):
+                cols = self._build_columns(raw, names, order)
+                if self._transform_spec:
+                    cols = self._apply_transform(cols, count)
+                done = torch.cuda.Event()
+                done.record()
+            self.rows_decoded += count
+            return GpuBatch(cols, count, [_EventWaiter(done), raw.decoded])
+
+        return PendingRowGroup(finalize, count)
+
+    def _load_rows(self, piece, shuffle_row_drop_partition):
+        return self._issue_rows(piece, shuffle_row_drop_partition).resolve()
 
     def _apply_transform(self, cols, count):
         spec = self._transform_spec
@@ -488,6 +510,26 @@ class GpuArrowWorker(_GpuWorkerBase):
             done = torch.cuda.Event()
             done.record()
         return GpuBatch(cols, int(keep.numel()), [_EventWaiter(done), raw_p.decoded, raw_o.decoded if raw_o else None])
+
+
+class PendingRowGroup(object):
+    """A row-group whose H2D copy and decode kernels have been *issued* by the pool thread but whose host-visible part
+    (error word, null counts, column views, codec / post-processing launches) is resolved by the consumer.  Publishing
+    these handles instead of finished batches keeps several row-groups in flight: the pool thread never blocks on the
+    device, so PCIe transfer, decode and the consumer overlap (the results queue bounds the depth)."""
+
+    def __init__(self, finalize, num_rows):
+        self._finalize = finalize
+        self._result = None
+        self._done = False
+        self.num_rows = num_rows
+
+    def resolve(self):
+        if not self._done:
+            self._result = self._finalize()
+            self._finalize = None
+            self._done = True
+        return self._result
 
 
 class _EventWaiter(object):
@@ -593,6 +635,18 @@ class GpuPyDictResultsQueueReader(object):
     def batched_output(self):
         return False
 
+    @staticmethod
+    def _next_group(workers_pool):
+        """Next non-empty decoded row-group (resolving handles of work issued ahead by the pool thread)."""
+        while True:
+            group = workers_pool.get_results()
+            if isinstance(group, PendingRowGroup):
+                group = group.resolve()
+                if group is None:
+                    continue
+            group.wait()
+            return group
+
     def read_next_rowgroup(self, workers_pool):
         """Whole (rest of the) current row-group as ``{field: column}`` with device tensors where they exist - the
         entry point of the batched loaders (no per-row namedtuples)."""
@@ -603,8 +657,7 @@ class GpuPyDictResultsQueueReader(object):
                     self._current = None
                     cols = {k: v[start:] for k, v in cur.columns.items()}
                 else:
-                    cur = workers_pool.get_results()
-                    cur.wait()
+                    cur = self._next_group(workers_pool)
                     self._current = None
                     cols = dict(cur.columns)
             return {k: (v.tensor if isinstance(v, ScalarColumn) else v) for k, v in cols.items()}
@@ -615,8 +668,7 @@ class GpuPyDictResultsQueueReader(object):
         try:
             with self._lock:
                 while self._current is None or self._next_index >= self._current.num_rows:
-                    self._current = workers_pool.get_results()
-                    self._current.wait()
+                    self._current = self._next_group(workers_pool)
                     self._next_index = 0
                 i = self._next_index
                 self._next_index += 1
@@ -646,20 +698,27 @@ class GpuPyDictWorker(_GpuWorkerBase):
         self._check_cache_usage(worker_predicate, shuffle_row_drop_partition)
         if worker_predicate:
             rows = self._load_rows_with_predicate(piece, worker_predicate, shuffle_row_drop_partition)
+        elif isinstance(self._local_cache, NullCache):
+            pending = self._issue_rows(piece, shuffle_row_drop_partition)   # asynchronous, resolved by the consumer
+            if pending.num_rows:
+                self.publish_func(pending)
+            return
         else:
             rows = self._local_cache.get(self._cache_key(piece, piece_index),
                                          lambda: self._load_rows(piece, shuffle_row_drop_partition))
-        if rows is None or rows.num_rows == 0:
-            return
-        if self._ngram:
-            result = self._form_ngram(rows)
-            if result.num_rows == 0:
-                return
-            self.rows_decoded += result.num_rows
+        result = self._finish_rows(rows)
+        if result is not None:
             self.publish_func(result)
-        else:
-            self.rows_decoded += rows.num_rows
-            self.publish_func(rows)
+
+    def _finish_rows(self, rows):
+        """NGram formation + accounting of a decoded row-group; None when nothing is left to publish."""
+        if rows is None or rows.num_rows == 0:
+            return None
+        result = self._form_ngram(rows) if self._ngram else rows
+        if result.num_rows == 0:
+            return None
+        self.rows_decoded += result.num_rows
+        return result
 
     # ---- shuffle: DataFrame.sample(frac=1, random_state=seed) (py_dict_reader_worker.py:269-270) ----------------
     def _shuffle_order(self, num_rows):
@@ -860,25 +919,44 @@ class GpuPyDictWorker(_GpuWorkerBase):
             raw.decoded.wait()
         return {name: self._decode_field(raw, name, self._schema.fields[name], order) for name in names}
 
-    def _load_rows(self, piece, shuffle_row_drop_partition):
+    def _issue_rows(self, piece, shuffle_row_drop_partition):
         names = [f.name for f in self._schema.fields.values()]
         raw = self._read_raw(piece, names)
         order = self._row_order(raw.num_rows, shuffle_row_drop_partition,
                                 self._ngram.length if self._ngram else 0)
+        count = raw.num_rows if order is None else len(order)
+
+        def finalize():
+            return self._finish_rows(self._decode_issued(raw, names, order, count))
+
+        return PendingRowGroup(finalize, count)
+
+    def _decode_issued(self, raw, names, order, count):
         with torch.cuda.stream(self._stream_of(raw)):
             cols = self._decode_all(raw, names, order)
-            count = raw.num_rows if order is None else len(order)
             if self._transform_spec:
                 cols = self._apply_transform(cols, count)
             done = torch.cuda.Event()
             done.record()
         return GpuRowGroupRows(cols, count, [_EventWaiter(done), raw.decoded])
 
+    def _load_rows(self, piece, shuffle_row_drop_partition):
+        names = [f.name for f in self._schema.fields.values()]
+        raw = self._read_raw(piece, names)
+        order = self._row_order(raw.num_rows, shuffle_row_drop_partition,
+                                self._ngram.length if self._ngram else 0)
+        return self._decode_issued(raw, names, order, raw.num_rows if order is None else len(order))
+
     def _apply_transform(self, cols, count):
         spec = self._transform_spec
         if spec.func:
             if spec.device:
+                scalar_types = {k: v.np_type for k, v in cols.items() if isinstance(v, ScalarColumn)}
                 cols = spec.func({k: (v.tensor if isinstance(v, ScalarColumn) else v) for k, v in cols.items()})
+                for k, np_type in scalar_types.items():   # untouched scalar columns keep their per-row numpy form
+                    if isinstance(cols.get(k), torch.Tensor) and cols[k].dim() == 1 and \
+                            _TORCH_OF_NUMPY.get(np.dtype(np_type)) == cols[k].dtype:
+                        cols[k] = ScalarColumn(cols[k], np_type)
             else:
                 # opaque user code: row dicts of host values, exactly what upstream passes
                 # (petastorm/py_dict_reader_worker.py:38-52)

@@ -134,9 +134,15 @@ class DataLoader(LoaderBase):
         else:
             self._shuffling_buffer = NoopShufflingBuffer()
         for row in self.reader:
-            row_as_dict = row._asdict()
+            if isinstance(row, dict):
+                # NGram window {offset: namedtuple} (extension: upstream's torch loader has no NGram support)
+                row_as_dict = {offset: item._asdict() for offset, item in row.items()}
+                for item in row_as_dict.values():
+                    _sanitize_pytorch_types(item)
+            else:
+                row_as_dict = row._asdict()
+                _sanitize_pytorch_types(row_as_dict)
             keys = row_as_dict.keys()
-            _sanitize_pytorch_types(row_as_dict)
             if not self.reader.batched_output:
                 self._shuffling_buffer.add_many([row_as_dict])
             else:
