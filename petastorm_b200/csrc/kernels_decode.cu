@@ -137,8 +137,8 @@ constexpr uint32_t kStageMask = kStage - 1;
 constexpr int kChunkShift = 11;
 constexpr uint32_t kChunk = 1u << kChunkShift;
 constexpr int kBatchOps = 32;
-constexpr uint32_t kBatchIn = 1024;   // a batch is closed after this many input bytes ...
-constexpr uint32_t kBatchOut = 4096;  // ... or this many output bytes
+constexpr uint32_t kBatchIn = 1024;   // a batch is closed after 32 elements or this many input bytes
+// (output per batch is bounded by the two limits above: 32 copies x 64 B + < 2 KiB of literals)
 constexpr uint32_t kBigLiteral = 1024;
 constexpr uint32_t kFlushBytes = 4096;
 constexpr uint32_t kLookahead = kBatchIn + kBigLiteral + 8;   // staged bytes a batch may touch past its start
@@ -163,6 +163,39 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) {
 }
 __device__ __forceinline__ void named_bar_arrive(int id, int count) {
     asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(count) : "memory");
+}
+// explicit shared-space accesses with 32-bit addresses: keeps generic->shared address conversions (S2R + LEA per
+// access, ~10% of the parser's instructions in profiles/r1_snappy_v3_parser_executor.txt) out of the serial chain
+// 32-bit shared-space address of a shared-memory object, computed once by an opaque asm so that the compiler cannot
+// re-materialise it (S2R SR_CgaCtaId + LEA, ~25 cycles) inside the serial loops
+__device__ __forceinline__ uint32_t shared_addr(const void *p) {
+    uint32_t a;
+    asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }\n" : "=r"(a) : "l"(p));
+    return a;
+}
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u8 [%0], %1;\n" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};\n" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
 constexpr int kBarFull = 1;    // +slot : P arrives, X syncs
 constexpr int kBarEmpty = 3;   // +slot : X arrives, P syncs
@@ -208,6 +241,8 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
         // ============================================ warp P =====================================================
         uint32_t ip = in_begin;
         uint32_t first_err = 0;
+        const uint32_t stage_s = shared_addr(stage);
+        const uint32_t batches_s = shared_addr(&batches[0]);
         {   // preamble: varint uncompressed length (a handful of bytes, read straight from global)
             uint64_t ulen = 0;
             int shift = 0;
@@ -234,7 +269,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                 keep_from = ip;
                 restart = false;
             }
-            SnBatch &bt = batches[s];
+            const uint32_t bt_s = batches_s + (uint32_t)s * (uint32_t)sizeof(SnBatch);
             // lane 0 decides (the flag may flip while the lanes read it): keeps the warp's control flow uniform
             const bool stop = __shfl_sync(0xffffffffu, (int)(abort_flag != 0 || first_err != 0), 0) != 0;
             if (!stop && ip < in_end && ip + kLookahead > ready_end && ready_end < in_end16) {
@@ -257,57 +292,82 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
             uint32_t n = 0, err = first_err, big = 0, big_len = 0;
             const uint32_t batch_start = ip;
             if (lane == 0 && !stop) {
-                uint32_t out_acc = 0;
+                // The serial chain.  A batch ends after 32 elements or 1 KiB of input, which also bounds its output
+                // (32 copies x 64 B + < 2 KiB of literals), so no per-element output accounting is needed.
                 const uint32_t lim = min(ip + kBatchIn, in_end);
-#define IN(p) stage[(p) & kStageMask]
-                while (n < (uint32_t)kBatchOps && ip < lim && out_acc < kBatchOut) {
-                    const uint32_t tag = IN(ip);
-                    uint32_t lo, hi;
-                    if ((tag & 3) == 0) {
-                        uint32_t len = (tag >> 2) + 1;
-                        uint32_t p = ip + 1;
-                        if (len > 60) {
-                            const uint32_t nb = len - 60;
-                            uint32_t v = 0;
-                            for (uint32_t i = 0; i < nb; i++) v |= (uint32_t)IN(p + i) << (8 * i);
-                            len = v + 1;
-                            p += nb;
+                uint32_t rec_s = bt_s;
+                const uint32_t rec_end = bt_s + kBatchOps * 8;
+#define IN(p) lds_u8(stage_s + ((p) & kStageMask))
+                // Branch-free common case: on a lone warp every taken branch costs ~15 cycles and every dependent ALU op
+                // ~5, so the element decode is written as selects; only copy-4 and literals with a length suffix (rare)
+                // leave the straight line.  The three header bytes are loaded together (one LDS latency).
+                if (ip < lim) {
+                    for (;;) {
+                        const uint32_t tag = IN(ip), b1 = IN(ip + 1), b2 = IN(ip + 2);
+                        uint32_t kind, t6, len, lo, used, flag, rare;
+                        // selects only (selp): ptxas would otherwise branch around the copy fields
+                        asm volatile(
+                            "{\n"
+                            " .reg .pred pl, p1, p3, pb;\n"
+                            " .reg .u32 lc, o1, o2, ul, uc;\n"
+                            " and.b32 %0, %7, 3;\n"
+                            " shr.u32 %1, %7, 2;\n"
+                            " setp.eq.u32 pl, %0, 0;\n"
+                            " setp.eq.u32 p1, %0, 1;\n"
+                            " setp.eq.u32 p3, %0, 3;\n"
+                            " add.u32 %2, %1, 1;\n"
+                            " and.b32 lc, %1, 7;\n"
+                            " add.u32 lc, lc, 4;\n"
+                            " selp.u32 %2, lc, %2, p1;\n"
+                            " shr.u32 o1, %7, 5;\n"
+                            " shl.b32 o1, o1, 8;\n"
+                            " or.b32 o1, o1, %8;\n"
+                            " shl.b32 o2, %9, 8;\n"
+                            " or.b32 o2, o2, %8;\n"
+                            " selp.u32 %3, o1, o2, p1;\n"
+                            " add.u32 ul, %10, 1;\n"
+                            " selp.u32 %3, ul, %3, pl;\n"
+                            " add.u32 ul, %1, 2;\n"
+                            " add.u32 uc, %0, 1;\n"
+                            " selp.u32 %4, ul, uc, pl;\n"
+                            " selp.u32 %5, 0, 0x1000000, pl;\n"
+                            " setp.ge.u32 pb, %1, 60;\n"
+                            " and.pred pb, pb, pl;\n"
+                            " or.pred pb, pb, p3;\n"
+                            " selp.u32 %6, 1, 0, pb;\n"
+                            "}\n"
+                            : "=r"(kind), "=r"(t6), "=r"(len), "=r"(lo), "=r"(used), "=r"(flag), "=r"(rare)
+                            : "r"(tag), "r"(b1), "r"(b2), "r"(ip));
+                        if (rare) {
+                            if (kind == 3) {
+                                lo = b1 | (b2 << 8) | (IN(ip + 3) << 16) | (IN(ip + 4) << 24);
+                                used = 5;
+                            } else {
+                                const uint32_t nb = t6 - 59;
+                                uint32_t v = 0;
+                                for (uint32_t i = 0; i < nb; i++) v |= IN(ip + 1 + i) << (8 * i);
+                                len = v + 1;
+                                lo = ip + 1 + nb;
+                                if (lo > in_end || len > in_end - lo) { err = 4; break; }
+                                if (len >= kBigLiteral) {
+                                    sts_v2(rec_s, lo, 2u << 24);
+                                    rec_s += 8;
+                                    big = 1;
+                                    big_len = len;
+                                    ip = lo + len;
+                                    break;
+                                }
+                                used = 1 + nb + len;
+                            }
                         }
-                        if (p > in_end || len > in_end - p || len > dst_n) { err = 4; break; }
-                        if (len >= kBigLiteral) {
-                            bt.rec[n++] = make_uint2(p, 2u << 24);
-                            big = 1;
-                            big_len = len;
-                            ip = p + len;
-                            break;
-                        }
-                        lo = p;
-                        hi = len;
-                        ip = p + len;
-                        out_acc += len;
-                    } else if ((tag & 3) == 1) {
-                        const uint32_t len = ((tag >> 2) & 7) + 4;
-                        lo = ((tag >> 5) << 8) | IN(ip + 1);
-                        hi = len | (1u << 24);
-                        ip += 2;
-                        out_acc += len;
-                    } else if ((tag & 3) == 2) {
-                        const uint32_t len = (tag >> 2) + 1;
-                        lo = (uint32_t)IN(ip + 1) | ((uint32_t)IN(ip + 2) << 8);
-                        hi = len | (1u << 24);
-                        ip += 3;
-                        out_acc += len;
-                    } else {
-                        const uint32_t len = (tag >> 2) + 1;
-                        lo = (uint32_t)IN(ip + 1) | ((uint32_t)IN(ip + 2) << 8) | ((uint32_t)IN(ip + 3) << 16) |
-                             ((uint32_t)IN(ip + 4) << 24);
-                        hi = len | (1u << 24);
-                        ip += 5;
-                        out_acc += len;
+                        sts_v2(rec_s, lo, len | flag);
+                        rec_s += 8;
+                        ip += used;
+                        if (!(rec_s < rec_end && ip < lim)) break;
                     }
-                    bt.rec[n++] = make_uint2(lo, hi);
                 }
 #undef IN
+                n = (rec_s - bt_s) >> 3;
                 if (!err && ip > in_end) err = 5;   // an element header ran past the end of the stream
             }
             n = __shfl_sync(0xffffffffu, n, 0);
@@ -316,12 +376,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
             big = __shfl_sync(0xffffffffu, big, 0);
             big_len = __shfl_sync(0xffffffffu, big_len, 0);
             const bool last = stop || err != 0 || ip >= in_end;
-            if (lane == 0) {
-                bt.n = n;
-                bt.err = err;
-                bt.last = last ? 1u : 0u;
-                bt.big_len = big_len;
-            }
+            if (lane == 0) sts_v4(bt_s + kBatchOps * 8, n, last ? 1u : 0u, err, big_len);
             keep_from = batch_start;
             if (big) restart = true;
             __syncwarp();
@@ -332,6 +387,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
         }
     } else {
         // ============================================ warp X =====================================================
+        const uint32_t ring_s = shared_addr(ring), stage_s = shared_addr(stage), batches_s = shared_addr(&batches[0]);
         uint32_t dst0 = 0;            // output position of the next batch
         uint32_t flushed = 0;         // output bytes already written to global memory
         uint32_t valid_from = 0;      // output positions below this are not in the ring (bypassed literal)
@@ -347,14 +403,15 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
         for (uint32_t b = 0;; b++) {
             const int s = b & 1;
             named_bar_sync(kBarFull + s, 64);
-            const SnBatch &bt = batches[s];
-            const uint32_t n = bt.n, last = bt.last, perr = bt.err, big_len = bt.big_len;
+            const uint32_t bt_s = batches_s + (uint32_t)s * (uint32_t)sizeof(SnBatch);
+            const uint4 hdr = lds_v4(bt_s + kBatchOps * 8);
+            const uint32_t n = hdr.x, last = hdr.y, perr = hdr.z, big_len = hdr.w;
             if (perr && !failed) {
                 failed = true;
                 if (lane == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, (int)perr);
             }
             if (!failed) {
-                const uint2 r = lane < (int)n ? bt.rec[lane] : make_uint2(0, 0);
+                const uint2 r = lane < (int)n ? lds_v2(bt_s + lane * 8) : make_uint2(0, 0);
                 const uint32_t kind = r.y >> 24;
                 const uint32_t a = r.x;
                 const uint32_t len = (lane < (int)n && kind != 2) ? (r.y & 0xffffffu) : 0u;
@@ -371,7 +428,8 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                     // ---- literals: staging -> ring.  Short ones per lane, longer ones by the whole warp.
                     const bool is_lit = lane < (int)n && kind == 0;
                     if (is_lit && len <= 16) {
-                        for (uint32_t i = 0; i < len; i++) ring[(d + i) & kRingMask] = stage[(a + i) & kStageMask];
+                        for (uint32_t i = 0; i < len; i++)
+                            sts_u8(ring_s + ((d + i) & kRingMask), lds_u8(stage_s + ((a + i) & kStageMask)));
                     }
                     uint32_t longs = __ballot_sync(0xffffffffu, is_lit && len > 16);
                     while (longs) {
@@ -380,7 +438,8 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                         const uint32_t bl = __shfl_sync(0xffffffffu, len, l);
                         const uint32_t bd = __shfl_sync(0xffffffffu, d, l);
                         const uint32_t ba = __shfl_sync(0xffffffffu, a, l);
-                        for (uint32_t i = lane; i < bl; i += 32) ring[(bd + i) & kRingMask] = stage[(ba + i) & kStageMask];
+                        for (uint32_t i = lane; i < bl; i += 32)
+                            sts_u8(ring_s + ((bd + i) & kRingMask), lds_u8(stage_s + ((ba + i) & kStageMask)));
                     }
                     __syncwarp();
                     // ---- back-references in dependency rounds
@@ -408,7 +467,8 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                         }
                         if (ready && in_ring) {
                             // sequential per lane: an overlapping copy (offset < length) re-reads its own bytes
-                            for (uint32_t i = 0; i < len; i++) ring[(d + i) & kRingMask] = ring[(d + i - a) & kRingMask];
+                            for (uint32_t i = 0; i < len; i++)
+                                sts_u8(ring_s + ((d + i) & kRingMask), lds_u8(ring_s + ((d + i - a) & kRingMask)));
                         }
                         pending &= ~__ballot_sync(0xffffffffu, ready);
                         __syncwarp();
