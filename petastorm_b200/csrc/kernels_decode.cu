@@ -137,20 +137,25 @@ constexpr uint32_t kStageMask = kStage - 1;
 constexpr int kChunkShift = 11;
 constexpr uint32_t kChunk = 1u << kChunkShift;
 constexpr int kBatchOps = 32;
-constexpr uint32_t kBatchIn = 1024;   // a batch is closed after 32 elements or this many input bytes
+constexpr uint32_t kBatchIn = 2048;   // >= input span of a batch without its last element (32 elements x <= 62 bytes)
 // (output per batch is bounded by the two limits above: 32 copies x 64 B + < 2 KiB of literals)
 constexpr uint32_t kBigLiteral = 1024;
 constexpr uint32_t kFlushBytes = 4096;
 constexpr uint32_t kLookahead = kBatchIn + kBigLiteral + 8;   // staged bytes a batch may touch past its start
 
 struct SnBatch {
-    uint2 rec[kBatchOps];   // .x = literal: input offset of the bytes | copy: back-reference offset
-                            // .y = length | kind << 24   (kind 0 literal, 1 copy, 2 bypassed big literal)
+    uint32_t pos[kBatchOps];  // input offset (from `gin`) of every element's tag byte: all the parser hands over
     uint32_t n;
-    uint32_t last;          // no batch follows
-    uint32_t err;           // parser error code (0 = ok)
-    uint32_t big_len;       // length of the kind-2 element (always the last of its batch)
+    uint32_t last;            // no batch follows
+    uint32_t err;             // parser error code (0 = ok)
+    uint32_t big_len;         // length of a bypassed big literal
+    uint32_t rare_a;          // the last element needed the slow path (copy-4 / literal with a length suffix):
+    uint32_t rare_h;          //   its decoded {source or offset, length | kind << 24}; rare_h == 0 when not present
+    uint32_t pad_[2];
 };
+static_assert(sizeof(SnBatch) == 160, "SnBatch layout");
+constexpr uint32_t kHdrOff = kBatchOps * 4;
+
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
@@ -179,6 +184,14 @@ __device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
 __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t x) {
+    asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(addr), "r"(x) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t x, uint32_t y) {
@@ -289,86 +302,74 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                 __syncwarp();
                 ready_end = issued_end;
             }
-            uint32_t n = 0, err = first_err, big = 0, big_len = 0;
+            uint32_t n = 0, err = first_err, big = 0, big_len = 0, rare_a = 0, rare_h = 0;
             const uint32_t batch_start = ip;
             if (lane == 0 && !stop) {
-                // The serial chain.  A batch ends after 32 elements or 1 KiB of input, which also bounds its output
-                // (32 copies x 64 B + < 2 KiB of literals), so no per-element output accounting is needed.
-                const uint32_t lim = min(ip + kBatchIn, in_end);
+                // The serial chain, kept to the bare minimum: the parser only finds where every element STARTS (that is
+                // the only thing that depends on the previous element); length, offset and kind are decoded by the
+                // executor lanes in parallel from the same staged bytes.  Per element: one LDS (tag), a select for
+                // the number of bytes consumed, one STS (position).  A batch ends after 32 elements (<= 32 x 62 bytes
+                // of input) or right after an element that needs the slow path (copy-4, literal with length suffix).
                 uint32_t rec_s = bt_s;
-                const uint32_t rec_end = bt_s + kBatchOps * 8;
-#define IN(p) lds_u8(stage_s + ((p) & kStageMask))
-                // Branch-free common case: on a lone warp every taken branch costs ~15 cycles and every dependent ALU op
-                // ~5, so the element decode is written as selects; only copy-4 and literals with a length suffix (rare)
-                // leave the straight line.  The three header bytes are loaded together (one LDS latency).
-                if (ip < lim) {
+                const uint32_t rec_end = bt_s + kBatchOps * 4;
+                if (ip < in_end) {
+#pragma unroll 4
                     for (;;) {
-                        const uint32_t tag = IN(ip), b1 = IN(ip + 1), b2 = IN(ip + 2);
-                        uint32_t kind, t6, len, lo, used, flag, rare;
-                        // selects only (selp): ptxas would otherwise branch around the copy fields
+                        const uint32_t tag = lds_u8(stage_s + (ip & kStageMask));
+                        uint32_t used, rare;
                         asm volatile(
                             "{\n"
-                            " .reg .pred pl, p1, p3, pb;\n"
-                            " .reg .u32 lc, o1, o2, ul, uc;\n"
-                            " and.b32 %0, %7, 3;\n"
-                            " shr.u32 %1, %7, 2;\n"
-                            " setp.eq.u32 pl, %0, 0;\n"
-                            " setp.eq.u32 p1, %0, 1;\n"
-                            " setp.eq.u32 p3, %0, 3;\n"
-                            " add.u32 %2, %1, 1;\n"
-                            " and.b32 lc, %1, 7;\n"
-                            " add.u32 lc, lc, 4;\n"
-                            " selp.u32 %2, lc, %2, p1;\n"
-                            " shr.u32 o1, %7, 5;\n"
-                            " shl.b32 o1, o1, 8;\n"
-                            " or.b32 o1, o1, %8;\n"
-                            " shl.b32 o2, %9, 8;\n"
-                            " or.b32 o2, o2, %8;\n"
-                            " selp.u32 %3, o1, o2, p1;\n"
-                            " add.u32 ul, %10, 1;\n"
-                            " selp.u32 %3, ul, %3, pl;\n"
-                            " add.u32 ul, %1, 2;\n"
-                            " add.u32 uc, %0, 1;\n"
-                            " selp.u32 %4, ul, uc, pl;\n"
-                            " selp.u32 %5, 0, 0x1000000, pl;\n"
-                            " setp.ge.u32 pb, %1, 60;\n"
+                            " .reg .pred pl, p3, pb;\n"
+                            " .reg .u32 kind, t6, ul, uc;\n"
+                            " and.b32 kind, %2, 3;\n"
+                            " shr.u32 t6, %2, 2;\n"
+                            " setp.eq.u32 pl, kind, 0;\n"
+                            " setp.eq.u32 p3, kind, 3;\n"
+                            " add.u32 ul, t6, 2;\n"
+                            " add.u32 uc, kind, 1;\n"
+                            " selp.u32 %0, ul, uc, pl;\n"
+                            " setp.ge.u32 pb, t6, 60;\n"
                             " and.pred pb, pb, pl;\n"
                             " or.pred pb, pb, p3;\n"
-                            " selp.u32 %6, 1, 0, pb;\n"
+                            " selp.u32 %1, 1, 0, pb;\n"
                             "}\n"
-                            : "=r"(kind), "=r"(t6), "=r"(len), "=r"(lo), "=r"(used), "=r"(flag), "=r"(rare)
-                            : "r"(tag), "r"(b1), "r"(b2), "r"(ip));
+                            : "=r"(used), "=r"(rare)
+                            : "r"(tag));
+                        sts_u32(rec_s, ip);
+                        rec_s += 4;
                         if (rare) {
-                            if (kind == 3) {
-                                lo = b1 | (b2 << 8) | (IN(ip + 3) << 16) | (IN(ip + 4) << 24);
-                                used = 5;
+#define IN(p) lds_u8(stage_s + ((p) & kStageMask))
+                            const uint32_t t6 = tag >> 2;
+                            if ((tag & 3) == 3) {
+                                rare_a = IN(ip + 1) | (IN(ip + 2) << 8) | (IN(ip + 3) << 16) | (IN(ip + 4) << 24);
+                                rare_h = (t6 + 1) | (1u << 24);
+                                ip += 5;
                             } else {
                                 const uint32_t nb = t6 - 59;
                                 uint32_t v = 0;
                                 for (uint32_t i = 0; i < nb; i++) v |= IN(ip + 1 + i) << (8 * i);
-                                len = v + 1;
-                                lo = ip + 1 + nb;
-                                if (lo > in_end || len > in_end - lo) { err = 4; break; }
+                                const uint32_t len = v + 1;
+                                const uint32_t p0 = ip + 1 + nb;
+                                if (p0 > in_end || len > in_end - p0) { err = 4; break; }
+                                rare_a = p0;
                                 if (len >= kBigLiteral) {
-                                    sts_v2(rec_s, lo, 2u << 24);
-                                    rec_s += 8;
+                                    rare_h = 2u << 24;
                                     big = 1;
                                     big_len = len;
-                                    ip = lo + len;
-                                    break;
+                                } else {
+                                    rare_h = len | (3u << 24);   // kind 3: staged literal with explicit length
                                 }
-                                used = 1 + nb + len;
+                                ip = p0 + len;
                             }
+#undef IN
+                            break;
                         }
-                        sts_v2(rec_s, lo, len | flag);
-                        rec_s += 8;
                         ip += used;
-                        if (!(rec_s < rec_end && ip < lim)) break;
+                        if (!(rec_s < rec_end && ip < in_end)) break;
                     }
                 }
-#undef IN
-                n = (rec_s - bt_s) >> 3;
-                if (!err && ip > in_end) err = 5;   // an element header ran past the end of the stream
+                n = (rec_s - bt_s) >> 2;
+                if (!err && ip > in_end) err = 5;   // an element ran past the end of the stream
             }
             n = __shfl_sync(0xffffffffu, n, 0);
             ip = __shfl_sync(0xffffffffu, ip, 0);
@@ -376,7 +377,10 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
             big = __shfl_sync(0xffffffffu, big, 0);
             big_len = __shfl_sync(0xffffffffu, big_len, 0);
             const bool last = stop || err != 0 || ip >= in_end;
-            if (lane == 0) sts_v4(bt_s + kBatchOps * 8, n, last ? 1u : 0u, err, big_len);
+            if (lane == 0) {
+                sts_v4(bt_s + kHdrOff, n, last ? 1u : 0u, err, big_len);
+                sts_v2(bt_s + kHdrOff + 16, rare_a, rare_h);
+            }
             keep_from = batch_start;
             if (big) restart = true;
             __syncwarp();
@@ -404,17 +408,34 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
             const int s = b & 1;
             named_bar_sync(kBarFull + s, 64);
             const uint32_t bt_s = batches_s + (uint32_t)s * (uint32_t)sizeof(SnBatch);
-            const uint4 hdr = lds_v4(bt_s + kBatchOps * 8);
+            const uint4 hdr = lds_v4(bt_s + kHdrOff);
             const uint32_t n = hdr.x, last = hdr.y, perr = hdr.z, big_len = hdr.w;
             if (perr && !failed) {
                 failed = true;
                 if (lane == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, (int)perr);
             }
             if (!failed) {
-                const uint2 r = lane < (int)n ? lds_v2(bt_s + lane * 8) : make_uint2(0, 0);
-                const uint32_t kind = r.y >> 24;
-                const uint32_t a = r.x;
-                const uint32_t len = (lane < (int)n && kind != 2) ? (r.y & 0xffffffu) : 0u;
+                // every lane decodes its own element from the staged bytes (the parser only located it)
+                uint32_t kind = 0, a = 0, len = 0;
+                if (lane < (int)n) {
+                    const uint2 rare = lds_v2(bt_s + kHdrOff + 16);
+                    if (lane == (int)n - 1 && rare.y != 0) {
+                        a = rare.x;
+                        kind = rare.y >> 24;           // 1 copy-4, 2 bypassed big literal, 3 long staged literal
+                        len = kind == 2 ? 0u : (rare.y & 0xffffffu);
+                        if (kind == 3) kind = 0;
+                    } else {
+                        const uint32_t pos = lds_u32(bt_s + lane * 4);
+                        const uint32_t tag = lds_u8(stage_s + (pos & kStageMask));
+                        const uint32_t b1 = lds_u8(stage_s + ((pos + 1) & kStageMask));
+                        const uint32_t b2 = lds_u8(stage_s + ((pos + 2) & kStageMask));
+                        const uint32_t t6 = tag >> 2;
+                        kind = tag & 3;
+                        if (kind == 0) { len = t6 + 1; a = pos + 1; }
+                        else if (kind == 1) { len = (t6 & 7) + 4; a = ((tag >> 5) << 8) | b1; }
+                        else { len = t6 + 1; a = b1 | (b2 << 8); kind = 1; }
+                    }
+                }
                 const uint32_t incl = warp_incl_scan(len, lane);
                 const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
                 const uint32_t d = dst0 + incl - len;          // output position of this lane's element
