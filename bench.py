@@ -200,6 +200,7 @@ def main():
         return
 
     # ----------------------------------------------------------------------------------------------------- B200 arm
+    import petastorm_b200  # noqa: F401  (first: sets CUDA_DEVICE_MAX_CONNECTIONS before the CUDA context exists)
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -234,7 +235,7 @@ def main():
     for i in mine:
         p = dec.plan(pieces[i].path, pieces[i].row_group, leaves)
         plans.append(p)
-        arenas.append(dec.upload(p))
+        arenas.append(dec.upload(p, private=True))
     torch.cuda.synchronize()
     payload = sum(p.info.payload_bytes for p in plans) / len(plans)   # encoded bytes E per row-group
     stream = dec.streams[0]
@@ -322,6 +323,8 @@ def main():
         host_buf.copy_(b.i00[:BATCH], non_blocking=True)
     barrier()
     h2d0 = reader.diagnostics['h2d_bytes']
+    if os.environ.get('PST_TRACE'):
+        rowgroup.TRACE = []
     rows_e2e = 0
     t0 = time.perf_counter()
     for k in range(args.steps):
@@ -339,6 +342,13 @@ def main():
     h2d = diag['h2d_bytes'] - h2d0
     reader.stop()
     reader.join()
+    if rowgroup.TRACE:
+        tr = rowgroup.TRACE
+        torch.cuda.synchronize()
+        h0, e0 = tr[0]
+        for h, ev in tr:
+            sys.stderr.write('issue %8.2f  h2d %8.2f .. %8.2f  decode .. %8.2f\n' % (
+                (h - h0) * 1e3, e0[0].elapsed_time(ev[0]), e0[0].elapsed_time(ev[1]), e0[0].elapsed_time(ev[2])))
     tw = torch.tensor([wall], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tw, op=dist.ReduceOp.MAX)
@@ -364,7 +374,8 @@ def main():
                 'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d // max(args.steps, 1),
                         'd2h_bytes_per_step': d2h // max(args.steps, 1), 'delivered_gbps': e2e_value * ROW_BYTES / 1e9,
                         'ms_per_step': 1e3 * wall / args.steps,
-                        'h2d_gbps': world * h2d / wall / 1e9, 'pinned_cache_hits': diag.get('pinned_cache_hits')},
+                        'h2d_gbps': world * h2d / wall / 1e9, 'pinned_cache_hits': diag.get('pinned_cache_hits'),
+                        'host_seconds_total': diag.get('host_seconds')},
                 'gpu_launches': gpu_launches, 'clocks': clocks}
         print(json.dumps(line))
     if world > 1:

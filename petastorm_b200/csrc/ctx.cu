@@ -1,8 +1,11 @@
 // Device half of the C-ABI: context (pinned staging / pinned row-group cache / host copy threads), upload, decode,
 // and the thin extern "C" wrappers around the post-processing kernels.
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <atomic>
+#include <cctype>
+#include <cstdlib>
 #include <condition_variable>
 #include <cstdio>
 #include <cstring>
@@ -31,11 +34,47 @@ inline void ck(cudaError_t e, const char *what) {
     if (e != cudaSuccess) throw CudaFail(std::string(what) + ": " + cudaGetErrorString(e));
 }
 
+// CPUs that are local (same NUMA node / PCIe root) to a CUDA device, from sysfs; empty when unknown.  Pinned staging
+// memory is allocated and filled from these CPUs so that the H2D DMA does not cross the socket interconnect.
+static std::vector<int> local_cpus_of_device(int device) {
+    std::vector<int> cpus;
+    char bus[64] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) return cpus;
+    for (char *c = bus; *c; c++) *c = (char)tolower(*c);
+    std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+    FILE *f = fopen(path.c_str(), "r");
+    if (!f) return cpus;
+    char line[4096] = {0};
+    if (fgets(line, sizeof line, f)) {
+        const char *p = line;
+        while (*p) {
+            char *e;
+            long a = strtol(p, &e, 10);
+            if (e == p) break;
+            long b = a;
+            if (*e == '-') { p = e + 1; b = strtol(p, &e, 10); }
+            for (long c = a; c <= b && c < CPU_SETSIZE; c++) cpus.push_back((int)c);
+            p = (*e == ',') ? e + 1 : e;
+            if (*e != ',') break;
+        }
+    }
+    fclose(f);
+    return cpus;
+}
+static bool pin_current_thread(const std::vector<int> &cpus, cpu_set_t *old) {
+    if (cpus.empty()) return false;
+    if (old && sched_getaffinity(0, sizeof(cpu_set_t), old) != 0) return false;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    for (int c : cpus) CPU_SET(c, &set);
+    return sched_setaffinity(0, sizeof set, &set) == 0;
+}
+
 // Minimal fork-join pool for the host-side staging copies (mmap -> pinned).
 class CopyPool {
 public:
-    explicit CopyPool(int n) {
-        for (int i = 0; i < n; i++) workers_.emplace_back([this] { run(); });
+    explicit CopyPool(int n, std::vector<int> cpus = {}) : cpus_(std::move(cpus)) {
+        for (int i = 0; i < n; i++) workers_.emplace_back([this] { pin_current_thread(cpus_, nullptr); run(); });
     }
     ~CopyPool() {
         {
@@ -95,6 +134,7 @@ private:
             work();
         }
     }
+    std::vector<int> cpus_;
     std::vector<std::thread> workers_;
     std::mutex m_;
     std::condition_variable cv_, done_cv_;
@@ -121,6 +161,7 @@ struct pst_ctx {
     PinnedBuf ring[3];
     int ring_next = 0;
     std::unique_ptr<CopyPool> pool;
+    std::vector<int> local_cpus;
     std::mutex mu;
     // counters
     std::atomic<int64_t> bytes_staged{0}, bytes_h2d{0}, cache_hits{0}, cache_misses{0}, pages_decoded{0},
@@ -160,6 +201,13 @@ static void fill_parallel(pst_ctx *c, const pst_plan *p, uint8_t *dst) {
     else for (int t = 0; t < n; t++) fn(t);
 }
 
+// A row-group's raw region goes up in ONE cudaMemcpyAsync: copies from different streams are served in submission
+// order, so each takes ~5 ms.  (Chunking them was tried: chunks of two row-groups interleave, every copy then takes
+// twice as long for the same PCIe throughput, and the decode behind it starts later.)
+static void h2d_copy(uint64_t d_dst, const uint8_t *src, int64_t n, cudaStream_t s) {
+    ck(cudaMemcpyAsync((void *)d_dst, src, (size_t)n, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync H2D");
+}
+
 extern "C" {
 
 int pst_has_cuda(void) { return 1; }
@@ -177,7 +225,8 @@ int pst_ctx_create(int device, int64_t pinned_cache_bytes, int copy_threads, pst
         unsigned hc = std::thread::hardware_concurrency();
         copy_threads = hc > 2 ? (int)std::min<unsigned>(hc - 1, 12) : 0;
     }
-    if (copy_threads > 0) c->pool.reset(new CopyPool(copy_threads));
+    c->local_cpus = local_cpus_of_device(device);
+    if (copy_threads > 0) c->pool.reset(new CopyPool(copy_threads, c->local_cpus));
     *out = c.release();
     return 0;
     PST_CATCH(1)
@@ -223,6 +272,13 @@ int pst_plan_upload(pst_ctx *c, pst_plan *p, uint64_t d_arena, uint64_t stream) 
         c->cache_hits++;
     } else {
         c->cache_misses++;
+        // allocate + first-touch the pinned pages from a CPU next to the GPU (restored below)
+        cpu_set_t old_affinity;
+        const bool repinned = pin_current_thread(c->local_cpus, &old_affinity);
+        struct Restore {
+            bool on; cpu_set_t *old;
+            ~Restore() { if (on) sched_setaffinity(0, sizeof(cpu_set_t), old); }
+        } restore{repinned, &old_affinity};
         bool cacheable = c->cache_bytes + need <= c->cache_budget;
         PinnedBuf *slot;
         if (cacheable) {
@@ -248,13 +304,13 @@ int pst_plan_upload(pst_ctx *c, pst_plan *p, uint64_t d_arena, uint64_t stream) 
         c->bytes_staged += p->payload_bytes;
         src = slot->ptr;
         if (!cacheable) {
-            ck(cudaMemcpyAsync((void *)d_arena, src, (size_t)need, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync H2D");
+            h2d_copy(d_arena, src, need, s);
             ck(cudaEventRecord(slot->ev, s), "cudaEventRecord");
             c->bytes_h2d += need;
             return 0;
         }
     }
-    ck(cudaMemcpyAsync((void *)d_arena, src, (size_t)need, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync H2D");
+    h2d_copy(d_arena, src, need, s);
     c->bytes_h2d += need;
     return 0;
     PST_CATCH(1)

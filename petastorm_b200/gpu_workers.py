@@ -109,8 +109,10 @@ class _GpuWorkerBase(WorkerBase):
         self._options = args[12] if len(args) > 12 and args[12] is not None else WorkerOptions()
         self._rng = np.random.default_rng(self._random_seed)
         self._decoder = None
+        self._post_stream = None
         self.rows_decoded = 0
         self.payload_bytes = 0
+        self.t_issue = self.t_wait = self.t_build = 0.0   # host seconds: issuing device work / waiting / building columns
 
     # ---- device decode of the requested fields ------------------------------------------------------------------
     def _get_decoder(self):
@@ -120,6 +122,8 @@ class _GpuWorkerBase(WorkerBase):
 
     def _read_raw(self, piece, field_names):
         """plan + H2D + device decode of the leaf columns behind `field_names` (partition columns excluded)."""
+        import time
+        t0 = time.perf_counter()
         dec = self._get_decoder()
         pfile = rowgroup.open_file(piece.path)
         partition_names = self._options.partitions.partition_names if self._options.partitions else set()
@@ -146,11 +150,17 @@ class _GpuWorkerBase(WorkerBase):
             decoded = dec.decode(piece.path, piece.row_group, leaf_ids)
             self.payload_bytes += decoded.plan.info.payload_bytes
         pvals = {k: v for k, v in piece.partition_keys if k in field_names}
+        self.t_issue += time.perf_counter() - t0
         return _RawRowGroup(piece, decoded, pfile.schema, name_to_slot, pvals, num_rows)
 
     def _stream_of(self, raw):
-        """The side stream that decoded `raw` (post-processing is queued behind the decode on the same stream)."""
-        return raw.decoded.stream if raw.decoded is not None else self._get_decoder().stream
+        """The stream post-processing of a decoded row-group runs on.  Not the decode stream: by the time a row-group
+        is finalised, the issuing thread has already queued later row-groups (H2D + ~15 ms of decode) on that stream
+        and anything appended there - in particular the `done` event the consumer waits for - would sit behind them.
+        ``decoded.wait()`` (``_build_columns``) orders this stream after the row-group's own decode."""
+        if self._post_stream is None:
+            self._post_stream = torch.cuda.Stream(self._get_decoder().device)
+        return self._post_stream
 
     # ---- row selection ------------------------------------------------------------------------------------------
     def _row_order(self, num_rows, shuffle_row_drop_partition, ngram_length=0):
@@ -206,7 +216,11 @@ class _GpuWorkerBase(WorkerBase):
 
     @property
     def diagnostics(self):
-        d = {'rows_decoded': self.rows_decoded, 'payload_bytes': self.payload_bytes}
+        d = {'rows_decoded': self.rows_decoded, 'payload_bytes': self.payload_bytes,
+             'host_seconds': {'issue': round(self.t_issue, 4), 'wait': round(self.t_wait, 4),
+                              'build': round(self.t_build, 4),
+                              'plan_upload_decode': [round(x, 4) for x in (self._decoder.host_seconds
+                                                                           if self._decoder else (0, 0, 0))]}}
         if self._decoder is not None:
             d['gpu_launches'] = self._decoder.launches
             d['h2d_bytes'] = self._decoder.h2d_bytes
@@ -318,6 +332,7 @@ class GpuBatch(object):
         for k in self._keepalive:
             if k is not None:
                 k.wait()
+        _record_on_current_stream(self.columns)
 
 
 class GpuArrowResultsQueueReader(object):
@@ -426,12 +441,17 @@ class GpuArrowWorker(_GpuWorkerBase):
         return self._transformed_schema if self._transform_spec else self._schema
 
     def _build_columns(self, raw, names, order):
+        import time
+        t0 = time.perf_counter()
         if raw.decoded is not None:
             raw.decoded.check()   # host sync: surfaces corrupt pages and delivers the per-column null counts
             raw.decoded.wait()
+        t1 = time.perf_counter()
         out = {}
         for name in names:
             out[name] = self._materialize(raw, name, self._schema.fields[name], order)
+        self.t_wait += t1 - t0
+        self.t_build += time.perf_counter() - t1
         return out
 
     def _issue_rows(self, piece, shuffle_row_drop_partition):
@@ -532,6 +552,15 @@ class PendingRowGroup(object):
         return self._result
 
 
+def _record_on_current_stream(columns):
+    """Columns were allocated on side streams; tell the caching allocator that the consumer's stream uses them."""
+    stream = torch.cuda.current_stream()
+    for v in columns.values():
+        t = v.tensor if isinstance(v, ScalarColumn) else v
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            t.record_stream(stream)
+
+
 class _EventWaiter(object):
     def __init__(self, event):
         self._event = event
@@ -596,6 +625,7 @@ class GpuRowGroupRows(object):
         for k in self._keepalive:
             if k is not None:
                 k.wait()
+        _record_on_current_stream(self.columns)
 
     def row(self, i, output):
         out = {}

@@ -47,7 +47,9 @@ def _make_cache(cache_type, cache_location, cache_size_limit, cache_row_size_est
 
 def _make_pool(reader_pool_type, workers_count, results_queue_size, device):
     if reader_pool_type in ('thread', 'process'):
-        return GpuPool(workers_count=1, results_queue_size=min(max(int(results_queue_size), 1), 4), device=device)
+        # `workers_count` here only sizes the ventilation window (2 * 4 = 8 row-groups in flight): deep enough to keep
+        # the PCIe copy engine busy while ~4 earlier row-groups are still in their (latency-bound) decode kernels
+        return GpuPool(workers_count=2, results_queue_size=min(max(int(results_queue_size), 1), 6), device=device)
     if reader_pool_type == 'dummy':
         return GpuPool(synchronous=True, device=device)
     raise ValueError('Unknown reader_pool_type: {}'.format(reader_pool_type))

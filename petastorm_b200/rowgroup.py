@@ -11,6 +11,8 @@ import threading
 from ctypes import byref, c_int
 
 import numpy as np
+import time
+
 import torch
 
 from petastorm_b200 import native
@@ -92,6 +94,10 @@ class DecodedColumn(object):
         return int(self.num_values - int(self.valid.sum().item()))
 
 
+# diagnostics: set to a list to collect (host time, [before H2D, after H2D, after decode] timing events) per row-group
+TRACE = None
+
+
 class DecodedRowGroup(object):
     def __init__(self, plan, arena, out, status, stream, device):
         self.plan = plan
@@ -102,7 +108,12 @@ class DecodedRowGroup(object):
         self.device = device
         self.num_rows = plan.info.num_rows
         self._checked = False
+        self.owns_arena = any(pc.physical_type == BYTE_ARRAY for pc in plan.cols)
         self.null_counts = None  # per plan column, filled by check()
+        with torch.cuda.stream(stream):
+            # the status words travel to pinned host memory on the decode stream, so check() needs no device copy
+            self.host_status = torch.empty(status.shape, dtype=status.dtype, pin_memory=True)
+            self.host_status.copy_(status, non_blocking=True)
         self.event = torch.cuda.Event()
         self.event.record(stream)
 
@@ -112,14 +123,20 @@ class DecodedRowGroup(object):
         stream.wait_event(self.event)
         # the buffers were allocated on the decode stream: tell the caching allocator about the consumer stream
         self.out.record_stream(stream)
-        self.arena.record_stream(stream)
+        if self.owns_arena:
+            self.arena.record_stream(stream)
 
     def check(self):
         """Host-synchronises with the decode and raises if a kernel reported a malformed page."""
         if self._checked:
             return
-        self.event.synchronize()
-        st = self.status.cpu().tolist()
+        # poll instead of cudaEventSynchronize: a host thread parked inside a blocking CUDA wait delays CUDA calls
+        # issued by the row-group issuing thread (measured: 6 ms per cudaEventRecord), which stalls the pipeline
+        spins = 0
+        while not self.event.query():
+            spins += 1
+            time.sleep(0 if spins < 50 else 0.0001)
+        st = self.host_status.tolist()
         self._checked = True
         self.null_counts = st[8:]
         if st[0] != 0:
@@ -158,18 +175,23 @@ class DecodedRowGroup(object):
 class RowGroupDecoder(object):
     """Issues plan -> upload -> decode for row-groups on side streams of one device."""
 
-    NUM_STREAMS = 3
+    NUM_STREAMS = 5
 
     def __init__(self, device=None):
         self.ctx = get_context(device)
         self.device = torch.device('cuda', self.ctx.device)
-        # consecutive row-groups go to different streams so that the serial tail of one row-group's decode (a few long
-        # Snappy streams) overlaps with the bulk of the next one
+        # consecutive row-groups go to different streams: a row-group's decode is latency-bound (~15 ms for 256 MB, the
+        # serial Snappy streams) while its H2D copy takes ~5 ms, so ~4 decodes must be in flight to keep PCIe busy
         self.streams = [torch.cuda.Stream(self.device) for _ in range(self.NUM_STREAMS)]
+        # one recyclable arena per stream: work on a stream is ordered, so the H2D copy of the next row-group may
+        # overwrite the arena as soon as it is *enqueued* behind the previous decode (numeric-only plans; BYTE_ARRAY
+        # columns keep pointing into their arena and get a private one)
+        self._stream_arena = {}
         self._next_stream = 0
         self.stream = self.streams[0]
         self.launches = 0
         self.h2d_bytes = 0
+        self.host_seconds = [0.0, 0.0, 0.0]  # plan / upload / decode-issue (diagnostics)
 
     def plan(self, path, row_group, leaf_columns):
         return native.Plan(open_file(path), row_group, leaf_columns)
@@ -180,11 +202,19 @@ class RowGroupDecoder(object):
         self.stream = s
         return s
 
-    def upload(self, plan, stream=None):
-        """H2D of a plan's raw region into a fresh arena; returns the arena tensor (async on `stream`)."""
+    def upload(self, plan, stream=None, private=False):
+        """H2D of a plan's raw region into an arena; returns the arena tensor (async on `stream`).  `private=True`
+        forces a dedicated arena (the caller wants to keep the raw bytes resident)."""
         stream = stream or self.stream
-        with torch.cuda.stream(stream):
-            arena = torch.empty(plan.info.arena_bytes, dtype=torch.uint8, device=self.device)
+        recyclable = not private and all(pc.physical_type != BYTE_ARRAY for pc in plan.cols)
+        key = stream.cuda_stream
+        arena = self._stream_arena.get(key) if recyclable else None
+        if arena is None or arena.numel() < plan.info.arena_bytes:
+            with torch.cuda.stream(stream):
+                arena = torch.empty(plan.info.arena_bytes + (plan.info.arena_bytes >> 3 if recyclable else 0),
+                                    dtype=torch.uint8, device=self.device)
+            if recyclable:
+                self._stream_arena[key] = arena
         native.check(native.lib.pst_plan_upload(self.ctx.handle, plan.handle, arena.data_ptr(),
                                                 stream.cuda_stream), 'pst_plan_upload')
         self.h2d_bytes += plan.info.raw_bytes
@@ -203,10 +233,26 @@ class RowGroupDecoder(object):
         return DecodedRowGroup(plan, arena, out, status, stream, self.device)
 
     def decode(self, path, row_group, leaf_columns):
+        t0 = time.perf_counter()
         plan = self.plan(path, row_group, leaf_columns)
         stream = self.next_stream()
+        t1 = time.perf_counter()
+        if TRACE is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record(stream)
         arena = self.upload(plan, stream)
-        return self.decode_resident(plan, arena, stream)
+        if TRACE is not None:
+            ev[1].record(stream)
+        t2 = time.perf_counter()
+        d = self.decode_resident(plan, arena, stream)
+        if TRACE is not None:
+            ev[2].record(stream)
+            TRACE.append((time.perf_counter(), ev))
+        t3 = time.perf_counter()
+        self.host_seconds[0] += t1 - t0
+        self.host_seconds[1] += t2 - t1
+        self.host_seconds[2] += t3 - t2
+        return d
 
 
 def gather_blobs_to_host(col, row_indices=None):

@@ -47,7 +47,8 @@ class GpuPool(object):
             raise RuntimeError('GpuPool({}) can not be reused! Create a new object'.format(self.workers_count))
         self._started = True
         self._ventilator_queue = queue.Queue()
-        self._results_queue = queue.Queue(self._results_queue_size + 1)
+        # every row-group occupies two entries (its result and its processed marker)
+        self._results_queue = queue.Queue(2 * self._results_queue_size + 1)
         publish = self._sync_results.append if self._synchronous else self._stop_aware_put
         self._worker = worker_class(0, publish, worker_args)
         if not self._synchronous:

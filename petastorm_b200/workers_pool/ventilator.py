@@ -8,8 +8,6 @@ Behaviours kept on purpose because seeded runs must reproduce the reference's or
 """
 import threading
 from abc import ABC, abstractmethod
-from time import sleep
-
 import numpy as np
 
 _VENTILATION_INTERVAL = 0.01
@@ -57,13 +55,18 @@ class ConcurrentVentilator(Ventilator):
         self._ventilated = 0
         self._processed = 0
         self._stop_requested = False
+        # back-pressure wake-up: the reference polls every `ventilation_interval` (10 ms) while the window is full,
+        # which is longer than a whole row-group decode here, so `processed_item` wakes the thread instead
+        self._window = threading.Condition()
 
     def start(self):
         self._thread = threading.Thread(target=self._run, name='pst-ventilator', daemon=True)
         self._thread.start()
 
     def processed_item(self):
-        self._processed += 1
+        with self._window:
+            self._processed += 1
+            self._window.notify()
 
     def completed(self):
         return self._stop_requested or self._iterations_remaining == 0 or not self._items
@@ -80,9 +83,10 @@ class ConcurrentVentilator(Ventilator):
             order = (self._rng if (self._seed is not None and self._seed != 0) else np.random).permutation(len(self._items))
             self._items = [self._items[i] for i in order]
         while not self.completed():
-            if self._ventilated - self._processed >= self._max_queue:
-                sleep(self._interval)
-                continue
+            with self._window:
+                if self._ventilated - self._processed >= self._max_queue:
+                    self._window.wait(self._interval)
+                    continue
             self._ventilate_fn(**self._items[self._cursor])
             self._cursor += 1
             self._ventilated += 1
@@ -93,6 +97,8 @@ class ConcurrentVentilator(Ventilator):
 
     def stop(self):
         self._stop_requested = True
+        with self._window:
+            self._window.notify()
         if self._thread is not None:
             self._thread.join()
             self._thread = None

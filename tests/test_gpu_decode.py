@@ -192,7 +192,7 @@ def test_corrupt_page_is_reported(tmp_path):
     pq.write_table(pa.table({'a': rng.integers(0, 1000, n)}), path, compression='snappy', use_dictionary=False)
     dec = rowgroup.RowGroupDecoder()
     plan = dec.plan(path, 0, [0])
-    arena = dec.upload(plan)
+    arena = dec.upload(plan, private=True)
     torch.cuda.synchronize()
     arena[100:4000] = 0xff  # trash the first page's snappy stream
     d = dec.decode_resident(plan, arena)
