@@ -283,31 +283,35 @@ def main():
     # ---- (2) roofline of the dominant kernel, per-kernel CUDA events on the launching stream ---------------------
     from ctypes import c_float
     from petastorm_b200 import native
-    ms_acc = np.zeros(3)
+    ms_acc = np.zeros(5)
     reps = max(4, min(args.steps, 8))
     for k in range(reps):
         j = k % len(plans)
         out = torch.empty(plans[j].info.out_bytes, dtype=torch.uint8, device=dev)
         status = torch.zeros(8 + len(leaves), dtype=torch.int32, device=dev)
-        ms3 = (c_float * 3)()
+        ms3 = (c_float * 5)()
         native.check(native.lib.pst_plan_decode_timed(dec.ctx.handle, plans[j].handle, arenas[j].data_ptr(),
                                                       out.data_ptr(), status.data_ptr(), stream.cuda_stream, ms3))
         ms_acc += np.array(list(ms3))
     ms_avg = ms_acc / reps
-    names = ['k_snappy_pages', 'k_ba_dict_index', 'k_decode_pages']
+    names = ['k_snappy_index', 'k_snappy_pages', 'k_snappy_pages(serial fallback)', 'k_ba_dict_index', 'k_decode_pages']
     dom = int(np.argmax(ms_avg))
     peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(peaks_path):
         peak, peak_src = json.load(open(peaks_path))['hbm_gbs'], 'measured (MEASURED_PEAKS.json hbm_gbs)'
     else:
         peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
-    algo_bytes = payload + rows_pg * ROW_BYTES          # E + D per launch (one launch = one row-group)
+    # algorithmic bytes per launch (one launch = one row-group): E = stored page bytes, U = uncompressed page images,
+    # D = decoded columns.  index: reads E; fragments: E -> U; page decode: U -> D.
+    U = plans[0].info.uncompressed_bytes
+    algo_by_kernel = [payload, payload + U, payload + U, 0, U + rows_pg * ROW_BYTES]
+    algo_bytes = algo_by_kernel[dom]
     achieved = algo_bytes / (ms_avg[dom] / 1e3) / 1e9
     roofline = {'bound': 'hbm', 'kernel': names[dom], 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': algo_bytes,
                 'kernel_ms': {n: float(m) for n, m in zip(names, ms_avg)},
-                'whole_decode_frac': algo_bytes / (float(ms_avg.sum()) / 1e3) / 1e9 / peak}
+                'whole_decode_frac': (payload + rows_pg * ROW_BYTES) / (float(ms_avg.sum()) / 1e3) / 1e9 / peak}
     del arenas, plans, keep, d
     torch.cuda.empty_cache()
 
@@ -323,8 +327,10 @@ def main():
         host_buf.copy_(b.i00[:BATCH], non_blocking=True)
     barrier()
     h2d0 = reader.diagnostics['h2d_bytes']
+    consumed = []
     if os.environ.get('PST_TRACE'):
         rowgroup.TRACE = []
+        consumed.append(time.perf_counter())
     rows_e2e = 0
     t0 = time.perf_counter()
     for k in range(args.steps):
@@ -334,6 +340,8 @@ def main():
             _ = b.f00[s:s + BATCH]
         host_buf.copy_(b.i00[:BATCH], non_blocking=True)   # device -> host read of the step's result
         torch.cuda.current_stream().synchronize()
+        if rowgroup.TRACE is not None:
+            consumed.append(time.perf_counter())
         d2h += host_buf.numel() * 8
         rows_e2e += n
     barrier()
@@ -349,6 +357,7 @@ def main():
         for h, ev in tr:
             sys.stderr.write('issue %8.2f  h2d %8.2f .. %8.2f  decode .. %8.2f\n' % (
                 (h - h0) * 1e3, e0[0].elapsed_time(ev[0]), e0[0].elapsed_time(ev[1]), e0[0].elapsed_time(ev[2])))
+        sys.stderr.write('consumed at: ' + ' '.join('%.1f' % ((c - h0) * 1e3) for c in consumed) + '\n')
     tw = torch.tensor([wall], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tw, op=dist.ReduceOp.MAX)

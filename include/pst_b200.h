@@ -142,9 +142,10 @@ int pst_plan_decode(pst_ctx *c, pst_plan *p, uint64_t d_arena, uint64_t d_out, u
                     int *launches);
 
 /* Measurement aid (bench.py roofline): the same launches with CUDA events between them on `stream`; synchronises and
- * writes the device milliseconds of {snappy, byte-array dictionary index, page decode} to ms3[0..2]. */
+ * writes the device milliseconds of {snappy fragment index, snappy fragments, snappy serial fallback, byte-array
+ * dictionary index, page decode} to ms5[0..4]. */
 int pst_plan_decode_timed(pst_ctx *c, pst_plan *p, uint64_t d_arena, uint64_t d_out, uint64_t d_status, uint64_t stream,
-                          float *ms3);
+                          float *ms5);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Column post-processing kernels (all async on `stream`; pointers are device addresses).

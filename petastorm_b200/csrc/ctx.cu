@@ -208,6 +208,37 @@ static void h2d_copy(uint64_t d_dst, const uint8_t *src, int64_t n, cudaStream_t
     ck(cudaMemcpyAsync((void *)d_dst, src, (size_t)n, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync H2D");
 }
 
+// Snappy: fragment index of the multi-fragment pages, every fragment of every page in parallel, serial fallback for
+// flagged pages.  Returns the number of launches; `ev` (optional, 4 events) brackets the three launches.
+static int launch_snappy_stage(pst_plan *p, uint8_t *arena, int32_t *status, cudaStream_t s, cudaEvent_t *ev) {
+    const DevPage *pages = (const DevPage *)(arena + p->pages_off);
+    const SnFrag *frags = (const SnFrag *)(arena + p->frag_list_off);
+    const int32_t *multi = (const int32_t *)(arena + p->multi_list_off);
+    uint32_t *frag_pos = (uint32_t *)(arena + p->frag_pos_off);
+    uint32_t *page_flag = (uint32_t *)(arena + p->page_flag_off);
+    const int n_frags = (int)p->snappy_frags.size(), n_multi = (int)p->multi_pages.size();
+    int nl = 0;
+    if (ev) ck(cudaEventRecord(ev[0], s), "record");
+    if (n_multi > 0) {
+        ck(launch_snappy_index(arena, pages, multi, n_multi, frag_pos, page_flag, s), "snappy index launch");
+        nl++;
+    }
+    if (ev) ck(cudaEventRecord(ev[1], s), "record");
+    if (n_frags > 0) {
+        ck(launch_snappy(arena, pages, frags, n_frags, multi, n_multi, frag_pos, page_flag, status, 0, s),
+           "snappy fragment launch");
+        nl++;
+    }
+    if (ev) ck(cudaEventRecord(ev[2], s), "record");
+    if (n_multi > 0) {
+        ck(launch_snappy(arena, pages, frags, n_frags, multi, n_multi, frag_pos, page_flag, status, 1, s),
+           "snappy fallback launch");
+        nl++;
+    }
+    if (ev) ck(cudaEventRecord(ev[3], s), "record");
+    return nl;
+}
+
 extern "C" {
 
 int pst_has_cuda(void) { return 1; }
@@ -325,14 +356,10 @@ int pst_plan_decode(pst_ctx *c, pst_plan *p, uint64_t d_arena, uint64_t d_out, u
     int32_t *status = (int32_t *)d_status;
     const DevCol *cols = (const DevCol *)(arena + p->cols_off);
     const DevPage *pages = (const DevPage *)(arena + p->pages_off);
-    const int32_t *comp = (const int32_t *)(arena + p->comp_list_off);
     const int32_t *data = (const int32_t *)(arena + p->data_list_off);
     const int32_t *dict = (const int32_t *)(arena + p->dict_list_off);
     int nl = 0;
-    if (!p->compressed_pages.empty()) {
-        ck(launch_snappy(arena, pages, comp, (int)p->compressed_pages.size(), status, s), "snappy launch");
-        nl++;
-    }
+    nl += launch_snappy_stage(p, arena, status, s, nullptr);
     if (!p->ba_dict_pages.empty()) {
         ck(launch_ba_dict_index(arena, pages, cols, dict, (int)p->ba_dict_pages.size(), status, s), "dict index launch");
         nl++;
@@ -352,29 +379,27 @@ int pst_plan_decode(pst_ctx *c, pst_plan *p, uint64_t d_arena, uint64_t d_out, u
 }
 
 // Same launches as pst_plan_decode with a CUDA event between them, on the launching stream; synchronises and reports
-// the device time of each kernel.  Measurement aid for bench.py's roofline numbers -- not used by the readers.
+// the device time of each kernel: ms[0..4] = Snappy fragment index, Snappy fragments, Snappy serial fallback,
+// BYTE_ARRAY dictionary index, page decode.  Measurement aid for bench.py's roofline numbers -- not used by the readers.
 int pst_plan_decode_timed(pst_ctx *c, pst_plan *p, uint64_t d_arena, uint64_t d_out, uint64_t d_status, uint64_t stream,
-                          float *ms3) {
+                          float *ms5) {
     PST_TRY
     (void)c;
     cudaStream_t s = (cudaStream_t)stream;
     uint8_t *arena = (uint8_t *)d_arena;
     const DevCol *cols = (const DevCol *)(arena + p->cols_off);
     const DevPage *pages = (const DevPage *)(arena + p->pages_off);
-    cudaEvent_t ev[4];
+    cudaEvent_t ev[6];
     for (auto &e : ev) ck(cudaEventCreate(&e), "cudaEventCreate");
-    ck(cudaEventRecord(ev[0], s), "record");
-    ck(launch_snappy(arena, pages, (const int32_t *)(arena + p->comp_list_off), (int)p->compressed_pages.size(),
-                     (int32_t *)d_status, s), "snappy launch");
-    ck(cudaEventRecord(ev[1], s), "record");
+    launch_snappy_stage(p, arena, (int32_t *)d_status, s, ev);
     ck(launch_ba_dict_index(arena, pages, cols, (const int32_t *)(arena + p->dict_list_off),
                             (int)p->ba_dict_pages.size(), (int32_t *)d_status, s), "dict index launch");
-    ck(cudaEventRecord(ev[2], s), "record");
+    ck(cudaEventRecord(ev[4], s), "record");
     ck(launch_decode_pages(arena, (uint8_t *)d_out, cols, pages, (const int32_t *)(arena + p->data_list_off),
                            (int)p->data_pages.size(), (int32_t *)d_status, s), "decode launch");
-    ck(cudaEventRecord(ev[3], s), "record");
-    ck(cudaEventSynchronize(ev[3]), "sync");
-    for (int i = 0; i < 3; i++) ck(cudaEventElapsedTime(&ms3[i], ev[i], ev[i + 1]), "elapsed");
+    ck(cudaEventRecord(ev[5], s), "record");
+    ck(cudaEventSynchronize(ev[5]), "sync");
+    for (int i = 0; i < 5; i++) ck(cudaEventElapsedTime(&ms5[i], ev[i], ev[i + 1]), "elapsed");
     for (auto &e : ev) cudaEventDestroy(e);
     return 0;
     PST_CATCH(1)

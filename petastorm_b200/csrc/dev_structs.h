@@ -20,6 +20,13 @@ enum DevErr : int32_t {
     DE_NGRAM_UNSORTED = 9, DE_BYTE_ARRAY_CORRUPT = 10
 };
 
+constexpr int32_t kSnappyFragment = 65536;
+
+struct SnFrag {             // one work item of the fragment decode kernel
+    int32_t page;           // page table index
+    int32_t k;              // fragment ordinal inside the page
+};
+
 struct DevPage {            // 64 bytes
     int64_t src_off;        // arena offset of the payload as stored in the file
     int64_t img_off;        // arena offset of the uncompressed page image (== src_off for uncompressed pages)
@@ -37,7 +44,11 @@ struct DevPage {            // 64 bytes
     uint8_t rep_enc;        // V1: Enc of repetition levels
     uint8_t v2_compressed;  // V2: values section compressed?
     int32_t page_ordinal;   // ordinal in file order inside the chunk (diagnostics)
-    int32_t pad_[3];
+    // Snappy pages: the compressed values are decoded as `nfrag` independent fragments of kSnappyFragment output bytes
+    // (the Snappy compressor restarts its match window every 64 KiB, see kernels_decode.cu)
+    int32_t frag_first;     // index of this page's first entry in the plan's fragment-position table (nfrag + 1 entries)
+    int32_t nfrag;          // fragments of this page (>= 1 for a compressed page, 0 otherwise)
+    int32_t multi_slot;     // index into the plan's multi-fragment page list / flag array, -1 when nfrag <= 1
 };
 static_assert(sizeof(DevPage) == 64, "DevPage must be 64 bytes");
 

@@ -319,6 +319,7 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
             if (h.type == 1) continue;  // INDEX_PAGE
             HostPage hp;
             memset(&hp.d, 0, sizeof hp.d);
+            hp.d.multi_slot = -1;
             hp.file_off = payload;
             DevPage &d = hp.d;
             d.comp_size = h.compressed_page_size;
@@ -381,6 +382,17 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
                 scratch_rel.push_back(rel);
                 scratch_cur = rel + d.uncomp_size + 16;  // +16: vector-store slack
                 p->compressed_pages.push_back((int32_t)p->pages.size());
+                // the compressed stream covers the whole image (V1) or everything behind the level bytes (V2)
+                const int64_t values_uncomp = (int64_t)d.uncomp_size -
+                                              (d.kind == PK_DATA_V2 ? (int64_t)d.def_bytes + d.rep_bytes : 0);
+                d.nfrag = (int32_t)std::max<int64_t>(1, (values_uncomp + kSnappyFragment - 1) / kSnappyFragment);
+                d.frag_first = (int32_t)p->frag_pos_count;
+                p->frag_pos_count += d.nfrag + 1;
+                if (d.nfrag > 1) {
+                    d.multi_slot = (int32_t)p->multi_pages.size();
+                    p->multi_pages.push_back((int32_t)p->pages.size());
+                }
+                for (int32_t k = 0; k < d.nfrag; k++) p->snappy_frags.push_back(SnFrag{(int32_t)p->pages.size(), k});
             } else {
                 d.src_off = align_up(raw_cur, 16) + phase;
                 raw_cur = d.src_off + d.comp_size + 16;  // +16: vector-load slack
@@ -409,8 +421,17 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
     p->comp_list_off = align_up(p->pages_off + (int64_t)sizeof(DevPage) * npages, 16);
     p->data_list_off = align_up(p->comp_list_off + 4 * (int64_t)p->compressed_pages.size(), 16);
     p->dict_list_off = align_up(p->data_list_off + 4 * (int64_t)p->data_pages.size(), 16);
-    p->raw_bytes = align_up(p->dict_list_off + 4 * (int64_t)p->ba_dict_pages.size(), 256);
+    p->frag_list_off = align_up(p->dict_list_off + 4 * (int64_t)p->ba_dict_pages.size(), 16);
+    p->multi_list_off = align_up(p->frag_list_off + (int64_t)sizeof(SnFrag) * (int64_t)p->snappy_frags.size(), 16);
+    p->raw_bytes = align_up(p->multi_list_off + 4 * (int64_t)p->multi_pages.size(), 256);
     p->scratch_off = p->raw_bytes;
+    {   // device-written tables of the Snappy fragment index (behind the page images)
+        int64_t rel = align_up(scratch_cur, 16);
+        p->frag_pos_off = p->scratch_off + rel;
+        rel = align_up(rel + 4 * p->frag_pos_count, 16);
+        p->page_flag_off = p->scratch_off + rel;
+        scratch_cur = rel + 4 * (int64_t)p->multi_pages.size();
+    }
     p->arena_bytes = align_up(p->scratch_off + scratch_cur + 256, 256);
 
     for (size_t i = 0; i < p->pages.size(); i++)
@@ -461,6 +482,10 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
         memcpy(t + (p->data_list_off - p->tables_off), p->data_pages.data(), 4 * p->data_pages.size());
     if (!p->ba_dict_pages.empty())
         memcpy(t + (p->dict_list_off - p->tables_off), p->ba_dict_pages.data(), 4 * p->ba_dict_pages.size());
+    if (!p->snappy_frags.empty())
+        memcpy(t + (p->frag_list_off - p->tables_off), p->snappy_frags.data(), sizeof(SnFrag) * p->snappy_frags.size());
+    if (!p->multi_pages.empty())
+        memcpy(t + (p->multi_list_off - p->tables_off), p->multi_pages.data(), 4 * p->multi_pages.size());
 
     // cache key: file identity + row group + column set
     uint64_t key = 1469598103934665603ull;

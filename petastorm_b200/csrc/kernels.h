@@ -17,8 +17,13 @@ constexpr int PST_BYTE_ARRAY_T = 6;
 constexpr int PST_FLBA_T = 7;
 
 cudaError_t configure_decode_kernels();
-cudaError_t launch_snappy(uint8_t *arena, const DevPage *pages, const int32_t *list, int n, int32_t *status,
-                          cudaStream_t s);
+// Snappy runs as up to three launches: fragment index of the multi-fragment pages, all fragments in parallel
+// (serial_mode 0), serial fallback for pages the first two flagged (serial_mode 1)
+cudaError_t launch_snappy_index(uint8_t *arena, const DevPage *pages, const int32_t *multi_list, int n_multi,
+                                uint32_t *frag_pos, uint32_t *page_flag, cudaStream_t s);
+cudaError_t launch_snappy(uint8_t *arena, const DevPage *pages, const SnFrag *frags, int n_frags,
+                          const int32_t *multi_list, int n_multi, const uint32_t *frag_pos, uint32_t *page_flag,
+                          int32_t *status, int serial_mode, cudaStream_t s);
 cudaError_t launch_ba_dict_index(uint8_t *arena, const DevPage *pages, const DevCol *cols, const int32_t *list, int n,
                                  int32_t *status, cudaStream_t s);
 cudaError_t launch_decode_pages(uint8_t *arena, uint8_t *out, const DevCol *cols, const DevPage *pages,

@@ -143,18 +143,22 @@ constexpr uint32_t kBigLiteral = 1024;
 constexpr uint32_t kFlushBytes = 4096;
 constexpr uint32_t kLookahead = kBatchIn + kBigLiteral + 8;   // staged bytes a batch may touch past its start
 
+constexpr int kHops = kBatchOps / 4;   // the parser advances four elements per step ("hop")
 struct SnBatch {
-    uint32_t pos[kBatchOps];  // input offset (from `gin`) of every element's tag byte: all the parser hands over
-    uint32_t n;
+    uint2 hop[kHops];         // {input offset of the hop's first tag byte, the byte lengths of its <= 4 elements}
+    uint32_t n;               // hop records in use
     uint32_t last;            // no batch follows
     uint32_t err;             // parser error code (0 = ok)
     uint32_t big_len;         // length of a bypassed big literal
-    uint32_t rare_a;          // the last element needed the slow path (copy-4 / literal with a length suffix):
-    uint32_t rare_h;          //   its decoded {source or offset, length | kind << 24}; rare_h == 0 when not present
+    uint32_t rare_a;          // the element after the last hop needed the slow path (copy-4 / literal with a length
+    uint32_t rare_h;          //   suffix): its decoded {source or offset, length | kind << 24}; rare_h == 0 when absent
     uint32_t pad_[2];
 };
-static_assert(sizeof(SnBatch) == 160, "SnBatch layout");
-constexpr uint32_t kHdrOff = kBatchOps * 4;
+static_assert(sizeof(SnBatch) == 96, "SnBatch layout");
+constexpr uint32_t kHdrOff = kHops * 8;
+// successor tables of the parser (see warp P)
+constexpr int kTabW = 1024;           // input positions covered by one table build (static shared memory <= 48 KiB)
+constexpr int kTabPad = 64;           // zero entries behind the window: an element is at most 61 bytes long
 
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
@@ -214,18 +218,37 @@ constexpr int kBarFull = 1;    // +slot : P arrives, X syncs
 constexpr int kBarEmpty = 3;   // +slot : X arrives, P syncs
 
 __global__ void __launch_bounds__(kSnappyThreads)
-k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, const int32_t *__restrict__ list,
-               int n_list, int32_t *status) {
+k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, const SnFrag *__restrict__ frags,
+               int n_frags, const int32_t *__restrict__ multi_list, int n_multi, const uint32_t *__restrict__ frag_pos,
+               uint32_t *page_flag, int32_t *status, int serial_mode) {
     // one allocation: the vector copies may read up to 15 bytes past the end of the ring (into the padding)
     __shared__ __align__(16) uint8_t smem_all[kRing + 16 + kStage];
     __shared__ __align__(16) SnBatch batches[2];
+    __shared__ __align__(16) uint32_t quad_tab[kTabW + kTabPad];
+    __shared__ __align__(16) uint8_t step_tab[kTabW + kTabPad];
+    __shared__ __align__(16) uint8_t step_lut[256];
     __shared__ volatile uint32_t abort_flag;
     uint8_t *const ring = smem_all;
     uint8_t *const stage = smem_all + kRing + 16;
+    // Work item.  serial_mode 0: one (page, fragment) pair of the plan's fragment list; fragments of a page whose
+    // index pass raised its flag are skipped.  serial_mode 1 (fallback launch): one multi-fragment page, decoded as a
+    // single stream, only if its flag is raised.
     const int li = blockIdx.x;
-    if (li >= n_list) return;
-    const int pi = list[li];
+    int pi, frag_k = 0;
+    if (serial_mode) {
+        if (li >= n_multi) return;
+        pi = multi_list[li];
+    } else {
+        if (li >= n_frags) return;
+        pi = frags[li].page;
+        frag_k = frags[li].k;
+    }
     const DevPage pg = pages[pi];
+    const bool fragmented = !serial_mode && pg.nfrag > 1;
+    if (pg.multi_slot >= 0) {
+        const uint32_t flag = *(volatile uint32_t *)&page_flag[pg.multi_slot];
+        if (serial_mode ? flag == 0 : flag != 0) return;
+    }
     const int lane = threadIdx.x & 31;
     const bool is_parser = threadIdx.x < 32;
 
@@ -234,12 +257,32 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
     uint32_t src_n = (uint32_t)pg.comp_size;
     uint32_t dst_n = (uint32_t)pg.uncomp_size;
     if (threadIdx.x == 0) abort_flag = 0;
+    // bytes an element occupies in the stream as a function of its tag; 0 = slow path (copy with 4-byte offset,
+    // literal with a length suffix)
+    for (int t = threadIdx.x; t < 256; t += kSnappyThreads) {
+        const int kind = t & 3, t6 = t >> 2;
+        step_lut[t] = (uint8_t)(kind == 0 ? (t6 < 60 ? t6 + 2 : 0) : kind == 1 ? 2 : kind == 2 ? 3 : 0);
+    }
+    for (int t = threadIdx.x; t < kTabPad; t += kSnappyThreads) {
+        step_tab[kTabW + t] = 0;
+        quad_tab[kTabW + t] = 0;
+    }
 
     // V2 data pages: the level bytes are stored uncompressed in front of the compressed values
     if (pg.kind == PK_DATA_V2) {
         uint32_t lv = (uint32_t)(pg.def_bytes + pg.rep_bytes);
-        if (!is_parser) coop_copy(dst, src, lv, lane, 32);
+        if (!is_parser && frag_k == 0) coop_copy(dst, src, lv, lane, 32);
         src += lv; dst += lv; src_n -= lv; dst_n -= lv;
+    }
+    const uint32_t full_n = dst_n;            // the length the stream's preamble must announce
+    const bool has_preamble = frag_k == 0;
+    if (fragmented) {
+        // [c0, c1) of the compressed values produce output bytes [k * 64 KiB, ...) (positions from k_snappy_index)
+        const uint32_t c0 = frag_pos[pg.frag_first + frag_k], c1 = frag_pos[pg.frag_first + frag_k + 1];
+        src += c0;
+        src_n = c1 - c0;
+        dst += (uint32_t)frag_k * (uint32_t)kSnappyFragment;
+        dst_n = min((uint32_t)kSnappyFragment, full_n - (uint32_t)frag_k * (uint32_t)kSnappyFragment);
     }
     __syncthreads();
     if ((int32_t)src_n <= 0) return;
@@ -256,7 +299,10 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
         uint32_t first_err = 0;
         const uint32_t stage_s = shared_addr(stage);
         const uint32_t batches_s = shared_addr(&batches[0]);
-        {   // preamble: varint uncompressed length (a handful of bytes, read straight from global)
+        const uint32_t quad_s = shared_addr(&quad_tab[0]), step_s = shared_addr(&step_tab[0]);
+        const uint32_t lut_s = shared_addr(&step_lut[0]);
+        uint32_t tab_w0 = 0, tab_end = 0;             // input window [tab_w0, tab_end) the tables describe
+        if (has_preamble) {   // varint uncompressed length (a handful of bytes, read straight from global)
             uint64_t ulen = 0;
             int shift = 0;
             for (;;) {
@@ -266,7 +312,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                 if (!(b & 0x80)) break;
                 shift += 7;
             }
-            if (!first_err && ulen != (uint64_t)dst_n) first_err = 2;
+            if (!first_err && ulen != (uint64_t)full_n) first_err = 2;
         }
         uint32_t issued_end = ip & ~(kChunk - 1);   // input bytes below this have been requested
         uint32_t ready_end = issued_end;            // input bytes below this are resident in `stage`
@@ -280,6 +326,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                 while (consumed[s ^ 1] < placed[s ^ 1]) { named_bar_sync(kBarEmpty + (s ^ 1), 64); consumed[s ^ 1]++; }
                 issued_end = ready_end = ip & ~(kChunk - 1);
                 keep_from = ip;
+                tab_w0 = tab_end = 0;
                 restart = false;
             }
             const uint32_t bt_s = batches_s + (uint32_t)s * (uint32_t)sizeof(SnBatch);
@@ -304,72 +351,101 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
             }
             uint32_t n = 0, err = first_err, big = 0, big_len = 0, rare_a = 0, rare_h = 0;
             const uint32_t batch_start = ip;
-            if (lane == 0 && !stop) {
-                // The serial chain, kept to the bare minimum: the parser only finds where every element STARTS (that is
-                // the only thing that depends on the previous element); length, offset and kind are decoded by the
-                // executor lanes in parallel from the same staged bytes.  Per element: one LDS (tag), a select for
-                // the number of bytes consumed, one STS (position).  A batch ends after 32 elements (<= 32 x 62 bytes
-                // of input) or right after an element that needs the slow path (copy-4, literal with length suffix).
-                uint32_t rec_s = bt_s;
-                const uint32_t rec_end = bt_s + kBatchOps * 4;
-                if (ip < in_end) {
+            // ---- successor tables.  Finding where the elements START is the only serial part of Snappy: the position
+            // of a tag depends on the element before it.  Instead of decoding tag after tag on that chain (~130 cycles
+            // per element for a lone lane), all 32 lanes first compute, for EVERY byte position of a 1 KiB window, how
+            // long an element starting there would be (step_tab, via a 256-entry lookup of the tag byte) and from that
+            // the lengths of the four consecutive elements that follow each position (quad_tab).  The chain is then
+            // one shared-memory load + one dp4a per FOUR elements.  Positions that start a slow-path element, lie
+            // behind the window or behind the end of the stream have length 0, which stops the walk there.
+            bool covered = !stop && ip < in_end && ip >= tab_w0 && ip < tab_end;
+            if (!stop && ip < in_end && !covered) {
+                const uint32_t tag0 = lds_u8(stage_s + (ip & kStageMask));
+                if (lds_u8(lut_s + tag0) != 0) {   // a window that starts with a slow-path element is not worth a build
+                    const uint32_t w0 = ip & ~3u;
 #pragma unroll 4
+                    for (int k = 0; k < kTabW / 128; k++) {
+                        const uint32_t wi = (uint32_t)lane + 32u * (uint32_t)k;
+                        const uint32_t pos = w0 + 4u * wi;
+                        const uint32_t word = lds_u32(stage_s + (pos & kStageMask));
+                        uint32_t st = lds_u8(lut_s + (word & 0xffu)) | (lds_u8(lut_s + ((word >> 8) & 0xffu)) << 8) |
+                                      (lds_u8(lut_s + ((word >> 16) & 0xffu)) << 16) | (lds_u8(lut_s + (word >> 24)) << 24);
+                        const int32_t nv = (int32_t)(in_end - pos);
+                        if (nv < 4) st = nv <= 0 ? 0u : (st & ((1u << (8 * nv)) - 1u));
+                        sts_u32(step_s + 4u * wi, st);
+                    }
+                    __syncwarp();
+#pragma unroll 4
+                    for (int k = 0; k < kTabW / 32; k++) {
+                        const uint32_t p0 = (uint32_t)lane + 32u * (uint32_t)k;
+                        const uint32_t s1 = lds_u8(step_s + p0);
+                        const uint32_t p1 = p0 + s1;
+                        const uint32_t s2 = lds_u8(step_s + p1);   // s1 == 0 re-reads the same 0: zeros propagate
+                        const uint32_t p2 = p1 + s2;
+                        const uint32_t s3 = lds_u8(step_s + p2);
+                        const uint32_t s4 = lds_u8(step_s + p2 + s3);
+                        sts_u32(quad_s + 4u * p0, s1 | (s2 << 8) | (s3 << 16) | (s4 << 24));
+                    }
+                    __syncwarp();
+                    tab_w0 = w0;
+                    tab_end = w0 + kTabW;
+                    covered = true;
+                }
+            }
+            if (lane == 0 && !stop && ip < in_end) {
+                uint32_t rec_s = bt_s;
+                const uint32_t rec_end = bt_s + kHops * 8;
+                bool at_stop = !covered;      // the walk ended on a position whose element length is 0
+                if (covered) {
+                    const uint32_t qbase = quad_s - (tab_w0 << 2);
                     for (;;) {
-                        const uint32_t tag = lds_u8(stage_s + (ip & kStageMask));
-                        uint32_t used, rare;
-                        asm volatile(
-                            "{\n"
-                            " .reg .pred pl, p3, pb;\n"
-                            " .reg .u32 kind, t6, ul, uc;\n"
-                            " and.b32 kind, %2, 3;\n"
-                            " shr.u32 t6, %2, 2;\n"
-                            " setp.eq.u32 pl, kind, 0;\n"
-                            " setp.eq.u32 p3, kind, 3;\n"
-                            " add.u32 ul, t6, 2;\n"
-                            " add.u32 uc, kind, 1;\n"
-                            " selp.u32 %0, ul, uc, pl;\n"
-                            " setp.ge.u32 pb, t6, 60;\n"
-                            " and.pred pb, pb, pl;\n"
-                            " or.pred pb, pb, p3;\n"
-                            " selp.u32 %1, 1, 0, pb;\n"
-                            "}\n"
-                            : "=r"(used), "=r"(rare)
-                            : "r"(tag));
-                        sts_u32(rec_s, ip);
-                        rec_s += 4;
-                        if (rare) {
-#define IN(p) lds_u8(stage_s + ((p) & kStageMask))
-                            const uint32_t t6 = tag >> 2;
-                            if ((tag & 3) == 3) {
-                                rare_a = IN(ip + 1) | (IN(ip + 2) << 8) | (IN(ip + 3) << 16) | (IN(ip + 4) << 24);
-                                rare_h = (t6 + 1) | (1u << 24);
-                                ip += 5;
-                            } else {
-                                const uint32_t nb = t6 - 59;
-                                uint32_t v = 0;
-                                for (uint32_t i = 0; i < nb; i++) v |= IN(ip + 1 + i) << (8 * i);
-                                const uint32_t len = v + 1;
-                                const uint32_t p0 = ip + 1 + nb;
-                                if (p0 > in_end || len > in_end - p0) { err = 4; break; }
-                                rare_a = p0;
-                                if (len >= kBigLiteral) {
-                                    rare_h = 2u << 24;
-                                    big = 1;
-                                    big_len = len;
-                                } else {
-                                    rare_h = len | (3u << 24);   // kind 3: staged literal with explicit length
-                                }
-                                ip = p0 + len;
-                            }
-#undef IN
+                        const uint32_t q = lds_u32(qbase + (ip << 2));
+                        sts_v2(rec_s, ip, q);
+                        ip = __dp4a(q, 0x01010101u, ip);          // ip += the four element lengths
+                        if (q < 0x01000000u) {                    // fewer than four elements: the walk stops here
+                            if (q != 0) rec_s += 8;
+                            at_stop = true;
                             break;
                         }
-                        ip += used;
-                        if (!(rec_s < rec_end && ip < in_end)) break;
+                        rec_s += 8;
+                        if (rec_s == rec_end) break;
                     }
                 }
-                n = (rec_s - bt_s) >> 2;
-                if (!err && ip > in_end) err = 5;   // an element ran past the end of the stream
+                n = (rec_s - bt_s) >> 3;
+                if (at_stop && ip < in_end && (!covered || ip < tab_end) && n < (uint32_t)kHops) {
+                    // slow-path element (behind a window end the next batch builds a new table instead)
+#define IN(p) lds_u8(stage_s + ((p) & kStageMask))
+                    const uint32_t tag = IN(ip);
+                    const uint32_t t6 = tag >> 2;
+                    if ((tag & 3) == 3) {
+                        rare_a = IN(ip + 1) | (IN(ip + 2) << 8) | (IN(ip + 3) << 16) | (IN(ip + 4) << 24);
+                        rare_h = (t6 + 1) | (1u << 24);
+                        ip += 5;
+                    } else if ((tag & 3) == 0 && t6 >= 60) {
+                        const uint32_t nb = t6 - 59;
+                        uint32_t v = 0;
+                        for (uint32_t i = 0; i < nb; i++) v |= IN(ip + 1 + i) << (8 * i);
+                        const uint32_t len = v + 1;
+                        const uint32_t p0 = ip + 1 + nb;
+                        if (p0 > in_end || len > in_end - p0) {
+                            err = 4;
+                        } else {
+                            rare_a = p0;
+                            if (len >= kBigLiteral) {
+                                rare_h = 2u << 24;
+                                big = 1;
+                                big_len = len;
+                            } else {
+                                rare_h = len | (3u << 24);   // kind 3: staged literal with explicit length
+                            }
+                            ip = p0 + len;
+                        }
+                    } else {
+                        err = 6;   // unreachable: a fast-path tag has a non-zero length inside the window
+                    }
+#undef IN
+                }
+                if (!err && ip > in_end) err = 5;   // a slow-path element ran past the end of the stream
             }
             n = __shfl_sync(0xffffffffu, n, 0);
             ip = __shfl_sync(0xffffffffu, ip, 0);
@@ -415,39 +491,55 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                 if (lane == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, (int)perr);
             }
             if (!failed) {
-                // every lane decodes its own element from the staged bytes (the parser only located it)
+                // every lane decodes its own element from the staged bytes (the parser only located the hops): lane l
+                // takes element l & 3 of hop l >> 2; the slow-path element, if any, goes to the lane after the last hop
                 uint32_t kind = 0, a = 0, len = 0;
-                if (lane < (int)n) {
-                    const uint2 rare = lds_v2(bt_s + kHdrOff + 16);
-                    if (lane == (int)n - 1 && rare.y != 0) {
+                bool have = false, overrun = false;
+                const uint2 rare = lds_v2(bt_s + kHdrOff + 16);
+                {
+                    const int h = lane >> 2, j = lane & 3;
+                    if (h < (int)n) {
+                        const uint2 hp = lds_v2(bt_s + h * 8);
+                        if ((hp.y >> (8 * j)) & 0xffu) {
+                            const uint32_t pos = __dp4a(hp.y & ((1u << (8 * j)) - 1u), 0x01010101u, hp.x);
+                            const uint32_t tag = lds_u8(stage_s + (pos & kStageMask));
+                            const uint32_t b1 = lds_u8(stage_s + ((pos + 1) & kStageMask));
+                            const uint32_t b2 = lds_u8(stage_s + ((pos + 2) & kStageMask));
+                            const uint32_t t6 = tag >> 2;
+                            kind = tag & 3;
+                            have = true;
+                            overrun = pos + ((hp.y >> (8 * j)) & 0xffu) > in_end;
+                            if (kind == 0) { len = t6 + 1; a = pos + 1; }
+                            else if (kind == 1) { len = (t6 & 7) + 4; a = ((tag >> 5) << 8) | b1; }
+                            else { len = t6 + 1; a = b1 | (b2 << 8); kind = 1; }
+                        }
+                    } else if (lane == 4 * (int)n && rare.y != 0) {
                         a = rare.x;
                         kind = rare.y >> 24;           // 1 copy-4, 2 bypassed big literal, 3 long staged literal
                         len = kind == 2 ? 0u : (rare.y & 0xffffffu);
                         if (kind == 3) kind = 0;
-                    } else {
-                        const uint32_t pos = lds_u32(bt_s + lane * 4);
-                        const uint32_t tag = lds_u8(stage_s + (pos & kStageMask));
-                        const uint32_t b1 = lds_u8(stage_s + ((pos + 1) & kStageMask));
-                        const uint32_t b2 = lds_u8(stage_s + ((pos + 2) & kStageMask));
-                        const uint32_t t6 = tag >> 2;
-                        kind = tag & 3;
-                        if (kind == 0) { len = t6 + 1; a = pos + 1; }
-                        else if (kind == 1) { len = (t6 & 7) + 4; a = ((tag >> 5) << 8) | b1; }
-                        else { len = t6 + 1; a = b1 | (b2 << 8); kind = 1; }
+                        have = true;
                     }
                 }
                 const uint32_t incl = warp_incl_scan(len, lane);
                 const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
                 const uint32_t d = dst0 + incl - len;          // output position of this lane's element
-                const bool is_copy = lane < (int)n && kind == 1;
-                bool bad = (d + len > dst_n) || (is_copy && (a == 0 || a > d));
+                const bool is_copy = have && kind == 1;
+                const bool cross = is_copy && a > d;      // source in front of this stream's first output byte
+                bool bad = overrun || (d + len > dst_n) || (is_copy && a == 0) || (cross && frag_k == 0);
                 if (__any_sync(0xffffffffu, bad)) {
                     failed = true;
                     abort_flag = 1;
                     if (lane == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, 8);
+                } else if (__any_sync(0xffffffffu, cross)) {
+                    // a back-reference into an earlier fragment: legal Snappy, just not what the reference compressor
+                    // emits.  The page is handed to the serial fallback launch, which rewrites its whole image.
+                    failed = true;
+                    abort_flag = 1;
+                    if (lane == 0) *(volatile uint32_t *)&page_flag[pg.multi_slot] = 2;
                 } else {
                     // ---- literals: staging -> ring.  Short ones per lane, longer ones by the whole warp.
-                    const bool is_lit = lane < (int)n && kind == 0;
+                    const bool is_lit = have && kind == 0;
                     if (is_lit && len <= 16) {
                         for (uint32_t i = 0; i < len; i++)
                             sts_u8(ring_s + ((d + i) & kRingMask), lds_u8(stage_s + ((a + i) & kStageMask)));
@@ -496,8 +588,8 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                     }
                     dst0 += total;
                     // ---- bypassed big literal (always the last element of its batch)
-                    if (n > 0 && __shfl_sync(0xffffffffu, kind, (int)n - 1) == 2) {
-                        const uint32_t bsrc = __shfl_sync(0xffffffffu, a, (int)n - 1);
+                    if ((rare.y >> 24) == 2) {
+                        const uint32_t bsrc = rare.x;
                         if (dst0 + big_len > dst_n) {
                             failed = true;
                             abort_flag = 1;
@@ -525,6 +617,203 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                 return;
             }
             named_bar_arrive(kBarEmpty + s, 64);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K2a  Snappy fragment index.  The reference compressor (snappy::RawCompress, which Arrow's Parquet writer calls once
+// per page) works on 64 KiB blocks of input and restarts its match window at every block, so a page is a concatenation
+// of independently decodable fragments -- but the stream does not say where they start.  This kernel finds out:
+// it walks the element chain of a page (multi-fragment pages only) WITHOUT producing output and records the
+// compressed offset at which the output position reaches every multiple of 64 KiB.  k_snappy_pages then decodes all
+// fragments of all pages in parallel.  A page whose elements straddle a 64 KiB boundary, or whose stream is damaged,
+// gets its flag raised and is decoded as one stream by the serial fallback launch (which also reports the error).
+//
+// The walk is the serial part, so it is made as short as possible: four builder warps compute, for every byte position
+// of a 1 KiB input window, {bytes consumed, bytes produced} by the NEXT 16 ELEMENTS starting there (lookup of the tag
+// byte, then four rounds of pointer doubling T2[p] = T[p] + T[p + consumed(T[p])] in shared memory).  The walker lane
+// then needs one shared-memory load and two adds per 16 elements.  Positions holding a slow-path tag, behind the window
+// or behind the stream have {0, 0}, which stalls the chain there.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kIdxBuilders = 4;
+constexpr int kIdxThreads = 32 * (kIdxBuilders + 1);
+constexpr int kIdxW = 1024;
+constexpr int kIdxPad = 64;
+constexpr int kBarIdxFull = 1;                    // + builder : builder arrives, walker syncs
+constexpr int kBarIdxEmpty = 1 + kIdxBuilders;    // + builder : walker arrives, builder syncs
+
+__global__ void __launch_bounds__(kIdxThreads)
+k_snappy_index(const uint8_t *__restrict__ arena, const DevPage *__restrict__ pages,
+               const int32_t *__restrict__ multi_list, int n_multi, uint32_t *__restrict__ frag_pos,
+               uint32_t *__restrict__ page_flag) {
+    __shared__ __align__(16) uint32_t tab[kIdxBuilders][kIdxW + kIdxPad];
+    __shared__ __align__(16) uint32_t tmp[kIdxBuilders][kIdxW + kIdxPad];
+    __shared__ uint32_t lut[256];                  // tag -> (bytes consumed * 4) | (bytes produced << 16); 0 = slow path
+    __shared__ volatile uint32_t walker_ip;        // lower bound of the walker's position (lets builders skip windows)
+    __shared__ volatile uint32_t give_up;
+    const int li = blockIdx.x;
+    if (li >= n_multi) return;
+    const int pi = multi_list[li];
+    const DevPage pg = pages[pi];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    const uint8_t *src = arena + pg.src_off;
+    uint32_t src_n = (uint32_t)pg.comp_size;
+    uint32_t dst_n = (uint32_t)pg.uncomp_size;
+    if (pg.kind == PK_DATA_V2) {
+        const uint32_t lv = (uint32_t)(pg.def_bytes + pg.rep_bytes);
+        src += lv; src_n -= lv; dst_n -= lv;
+    }
+    const uint8_t *gin = src - ((uintptr_t)src & 15);
+    const uint32_t in_begin = (uint32_t)((uintptr_t)src & 15);
+    const uint32_t in_end = in_begin + src_n;
+    const uint32_t in_end16 = (in_end + 15) & ~15u;
+
+    for (int t = threadIdx.x; t < 256; t += kIdxThreads) {
+        const uint32_t kind = t & 3, t6 = t >> 2;
+        uint32_t used = 0, made = 0;
+        if (kind == 0) { if (t6 < 60) { used = t6 + 2; made = t6 + 1; } }
+        else if (kind == 1) { used = 2; made = (t6 & 7) + 4; }
+        else if (kind == 2) { used = 3; made = t6 + 1; }
+        lut[t] = (used << 2) | (made << 16);
+    }
+    for (int t = threadIdx.x; t < kIdxBuilders * kIdxPad; t += kIdxThreads) {
+        tab[t / kIdxPad][kIdxW + t % kIdxPad] = 0;
+        tmp[t / kIdxPad][kIdxW + t % kIdxPad] = 0;
+    }
+    if (threadIdx.x == 0) { walker_ip = in_begin; give_up = 0; }
+    __syncthreads();
+    const uint32_t nwin = (in_end + kIdxW - 1) / kIdxW;      // windows over positions [0, in_end), aligned to kIdxW
+
+    if (warp < kIdxBuilders) {
+        // ============================================ builders ===================================================
+        const uint32_t tab_s = shared_addr(&tab[warp][0]), tmp_s = shared_addr(&tmp[warp][0]);
+        const uint32_t lut_s = shared_addr(&lut[0]);
+        for (uint32_t j = (uint32_t)warp; j < nwin; j += kIdxBuilders) {
+            if (j >= (uint32_t)kIdxBuilders) named_bar_sync(kBarIdxEmpty + warp, 64);
+            const uint32_t w0 = j * kIdxW;
+            const bool skip = __shfl_sync(0xffffffffu, (int)(give_up != 0 || w0 + kIdxW <= walker_ip), 0) != 0;
+            if (!skip) {
+                // one element: every position as if a tag started there
+#pragma unroll 4
+                for (int k = 0; k < kIdxW / 128; k++) {
+                    const uint32_t wi = (uint32_t)lane + 32u * (uint32_t)k;
+                    const uint32_t pos = w0 + 4u * wi;
+                    uint32_t word = 0;
+                    if (pos < in_end16) word = __ldg(reinterpret_cast<const uint32_t *>(gin + pos));
+                    uint32_t e0 = lds_u32(lut_s + ((word & 0xffu) << 2));
+                    uint32_t e1 = lds_u32(lut_s + (((word >> 8) & 0xffu) << 2));
+                    uint32_t e2 = lds_u32(lut_s + (((word >> 16) & 0xffu) << 2));
+                    uint32_t e3 = lds_u32(lut_s + ((word >> 24) << 2));
+                    const int32_t nv = (int32_t)(in_end - pos);      // stream bytes in this word
+                    if (nv < 4) {
+                        if (nv < 1) e0 = 0;
+                        if (nv < 2) e1 = 0;
+                        if (nv < 3) e2 = 0;
+                        e3 = 0;
+                    }
+                    sts_v4(tab_s + 16u * wi, e0, e1, e2, e3);
+                }
+                __syncwarp();
+                // 2, 4, 8, 16 elements by pointer doubling (the low half of an entry is already a byte offset)
+                uint32_t from_s = tab_s, to_s = tmp_s;
+#pragma unroll 1
+                for (int r = 0; r < 4; r++) {
+#pragma unroll 8
+                    for (int k = 0; k < kIdxW / 32; k++) {
+                        const uint32_t a0 = from_s + 4u * ((uint32_t)lane + 32u * (uint32_t)k);
+                        const uint32_t e = lds_u32(a0);
+                        const uint32_t f = lds_u32(a0 + (e & 0xffffu));     // e == 0 re-reads itself: stalls stay
+                        sts_u32(a0 - from_s + to_s, e + f);
+                    }
+                    __syncwarp();
+                    const uint32_t t = from_s; from_s = to_s; to_s = t;
+                }
+            }
+            __threadfence_block();
+            named_bar_arrive(kBarIdxFull + warp, 64);
+        }
+    } else {
+        // ============================================ walker =====================================================
+        const uint32_t lut_s = shared_addr(&lut[0]);
+        uint32_t ip = in_begin, op = 0, next_b = (uint32_t)kSnappyFragment, k = 1, flag = 0;
+        uint32_t *const my_pos = frag_pos + pg.frag_first;
+        if (lane == 0) {
+            my_pos[0] = 0;
+            uint64_t ulen = 0;
+            int shift = 0;
+            for (;;) {
+                if (ip >= in_end || shift > 35) { flag = 1; break; }
+                const uint8_t b = gin[ip++];
+                ulen |= (uint64_t)(b & 0x7f) << shift;
+                if (!(b & 0x80)) break;
+                shift += 7;
+            }
+            if (ulen != (uint64_t)dst_n) flag = 1;
+            if (flag) give_up = 1;
+        }
+        for (uint32_t j = 0; j < nwin; j++) {
+            const int b = (int)(j % kIdxBuilders);
+            named_bar_sync(kBarIdxFull + b, 64);
+            const uint32_t wend = min((j + 1) * (uint32_t)kIdxW, in_end);
+            if (lane == 0 && !flag && ip < wend) {
+                const uint32_t base = shared_addr(&tab[b][0]) - ((j * (uint32_t)kIdxW) << 2);
+                for (;;) {
+                    const uint32_t e = lds_u32(base + (ip << 2));
+                    const uint32_t adv = e & 0xffffu;
+                    if (adv == 0) {
+                        if (ip >= wend) break;
+                        // slow-path element: its length is in the stream, not in the tag
+                        const uint32_t tag = gin[ip];
+                        uint32_t used, made;
+                        if ((tag & 3) == 3) { used = 5; made = (tag >> 2) + 1; }
+                        else if ((tag & 3) == 0 && (tag >> 2) >= 60) {
+                            const uint32_t nb = (tag >> 2) - 59;
+                            uint32_t v = 0;
+                            for (uint32_t i = 0; i < nb && ip + 1 + i < in_end; i++) v |= (uint32_t)gin[ip + 1 + i] << (8 * i);
+                            made = v + 1;
+                            used = 1 + nb + made;
+                            if (made > in_end - ip || used > in_end - ip) { flag = 1; break; }
+                        } else { flag = 1; break; }
+                        if (op == next_b && k < (uint32_t)pg.nfrag) { my_pos[k++] = ip - in_begin; next_b += kSnappyFragment; }
+                        else if (op < next_b && made > next_b - op) { flag = 1; break; }
+                        ip += used;
+                        op += made;
+                        if (ip >= wend) break;      // a long literal usually leaves the window (and several more)
+                        continue;
+                    }
+                    const uint32_t op2 = op + (e >> 16);
+                    if (op2 >= next_b) {
+                        // a fragment boundary lies in (or right behind) these 16 elements: take them one at a time
+                        const uint32_t hop_end = ip + (adv >> 2);
+                        while (ip < hop_end) {
+                            const uint32_t one = lds_u32(lut_s + ((uint32_t)gin[ip] << 2));
+                            const uint32_t made = one >> 16;
+                            if (one == 0) { flag = 1; break; }   // cannot happen: the table came from the same bytes
+                            if (op == next_b && k < (uint32_t)pg.nfrag) { my_pos[k++] = ip - in_begin; next_b += kSnappyFragment; }
+                            else if (op < next_b && made > next_b - op) { flag = 1; break; }
+                            ip += (one & 0xffffu) >> 2;
+                            op += made;
+                        }
+                        if (flag) break;
+                        continue;
+                    }
+                    ip += adv >> 2;
+                    op = op2;
+                }
+                if (flag) give_up = 1;
+            }
+            if (lane == 0) walker_ip = ip;
+            if (j + kIdxBuilders < nwin) {
+                __threadfence_block();
+                named_bar_arrive(kBarIdxEmpty + b, 64);
+            }
+        }
+        if (lane == 0) {
+            if (!flag && (ip != in_end || op != dst_n || k != (uint32_t)pg.nfrag)) flag = 1;
+            if (!flag) my_pos[pg.nfrag] = src_n;
+            page_flag[pg.multi_slot] = flag;
         }
     }
 }
@@ -979,10 +1268,20 @@ cudaError_t configure_decode_kernels() {
     return cudaFuncSetAttribute(k_decode_pages, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeShared));
 }
 
-cudaError_t launch_snappy(uint8_t *arena, const DevPage *pages, const int32_t *list, int n, int32_t *status,
-                          cudaStream_t s) {
+cudaError_t launch_snappy_index(uint8_t *arena, const DevPage *pages, const int32_t *multi_list, int n_multi,
+                                uint32_t *frag_pos, uint32_t *page_flag, cudaStream_t s) {
+    if (n_multi <= 0) return cudaSuccess;
+    k_snappy_index<<<n_multi, kIdxThreads, 0, s>>>(arena, pages, multi_list, n_multi, frag_pos, page_flag);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_snappy(uint8_t *arena, const DevPage *pages, const SnFrag *frags, int n_frags,
+                          const int32_t *multi_list, int n_multi, const uint32_t *frag_pos, uint32_t *page_flag,
+                          int32_t *status, int serial_mode, cudaStream_t s) {
+    const int n = serial_mode ? n_multi : n_frags;
     if (n <= 0) return cudaSuccess;
-    k_snappy_pages<<<n, kSnappyThreads, 0, s>>>(arena, pages, list, n, status);
+    k_snappy_pages<<<n, kSnappyThreads, 0, s>>>(arena, pages, frags, n_frags, multi_list, n_multi, frag_pos, page_flag,
+                                                 status, serial_mode);
     return cudaGetLastError();
 }
 
