@@ -413,6 +413,19 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
         }
     }
 
+    // Launch order of the Snappy work items: the better a page compressed, the more elements its stream has per output
+    // byte and the longer its fragments take; those go first so that the tail of the grid is made of short items.
+    auto ratio_less = [&](int32_t a, int32_t b) {
+        const DevPage &x = p->pages[a].d, &y = p->pages[b].d;
+        return (int64_t)x.comp_size * y.uncomp_size < (int64_t)y.comp_size * x.uncomp_size;
+    };
+    std::stable_sort(p->snappy_frags.begin(), p->snappy_frags.end(),
+                     [&](const SnFrag &a, const SnFrag &b) { return ratio_less(a.page, b.page); });
+    {   // same order for the index kernel; multi_slot follows the sorted list
+        std::stable_sort(p->multi_pages.begin(), p->multi_pages.end(), ratio_less);
+        for (size_t i = 0; i < p->multi_pages.size(); i++) p->pages[p->multi_pages[i]].d.multi_slot = (int32_t)i;
+    }
+
     // ---- tables at the tail of the raw region
     int64_t npages = (int64_t)p->pages.size();
     p->tables_off = align_up(raw_cur, 256);

@@ -130,7 +130,7 @@ __device__ __forceinline__ void coop_fill(uint8_t *dst, uint8_t v, int64_t n, in
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane);   // defined with the page decoder below
 
 constexpr int kSnappyThreads = 64;
-constexpr int kRing = 32768;          // power of two
+constexpr int kRing = 16384;          // power of two; with the tables below ~30 KiB of shared memory per CTA (7 CTAs/SM)
 constexpr uint32_t kRingMask = kRing - 1;
 constexpr int kStage = 8192;          // input staging window: 4 chunks of 2 KiB (power of two)
 constexpr uint32_t kStageMask = kStage - 1;
@@ -167,11 +167,25 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
-__device__ __forceinline__ void named_bar_sync(int id, int count) {
-    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory");
+// Named barriers with IMMEDIATE ids: with a register id ptxas reserves all 16 hardware barriers for the CTA, and the
+// 64 barriers of an SM then cap residency at 4 CTAs (launch__occupancy_limit_barriers in profiles/r1_snappy_v8).
+template <int ID>
+__device__ __forceinline__ void bar_sync_imm() { asm volatile("bar.sync %0, 64;\n" ::"n"(ID) : "memory"); }
+template <int ID>
+__device__ __forceinline__ void bar_arrive_imm() { asm volatile("bar.arrive %0, 64;\n" ::"n"(ID) : "memory"); }
+template <int BASE, int N>
+__device__ __forceinline__ void named_bar_sync(int k) {      // barrier BASE + k, k in [0, N), 64 participants
+    if (k == 0) bar_sync_imm<BASE>();
+    if (N > 1 && k == 1) bar_sync_imm<BASE + 1>();
+    if (N > 2 && k == 2) bar_sync_imm<BASE + 2>();
+    if (N > 3 && k == 3) bar_sync_imm<BASE + 3>();
 }
-__device__ __forceinline__ void named_bar_arrive(int id, int count) {
-    asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(count) : "memory");
+template <int BASE, int N>
+__device__ __forceinline__ void named_bar_arrive(int k) {
+    if (k == 0) bar_arrive_imm<BASE>();
+    if (N > 1 && k == 1) bar_arrive_imm<BASE + 1>();
+    if (N > 2 && k == 2) bar_arrive_imm<BASE + 2>();
+    if (N > 3 && k == 3) bar_arrive_imm<BASE + 3>();
 }
 // explicit shared-space accesses with 32-bit addresses: keeps generic->shared address conversions (S2R + LEA per
 // access, ~10% of the parser's instructions in profiles/r1_snappy_v3_parser_executor.txt) out of the serial chain
@@ -317,13 +331,15 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
         uint32_t issued_end = ip & ~(kChunk - 1);   // input bytes below this have been requested
         uint32_t ready_end = issued_end;            // input bytes below this are resident in `stage`
         uint32_t keep_from = ip;                    // start of the previous batch: X may still read literals from there
-        uint32_t placed[2] = {0, 0}, consumed[2] = {0, 0};
+        uint32_t owed0 = 0, owed1 = 0;               // batches handed to X and not yet released, per slot (0 or 1)
         bool restart = false;
         for (uint32_t b = 0;; b++) {
             const int s = b & 1;
-            while (consumed[s] < placed[s]) { named_bar_sync(kBarEmpty + s, 64); consumed[s]++; }
+            if (s == 0) { if (owed0) { bar_sync_imm<kBarEmpty>(); owed0 = 0; } }
+            else if (owed1) { bar_sync_imm<kBarEmpty + 1>(); owed1 = 0; }
             if (restart) {   // after a bypassed literal the staging window moves: wait until X is done with everything
-                while (consumed[s ^ 1] < placed[s ^ 1]) { named_bar_sync(kBarEmpty + (s ^ 1), 64); consumed[s ^ 1]++; }
+                if (s == 1) { if (owed0) { bar_sync_imm<kBarEmpty>(); owed0 = 0; } }
+                else if (owed1) { bar_sync_imm<kBarEmpty + 1>(); owed1 = 0; }
                 issued_end = ready_end = ip & ~(kChunk - 1);
                 keep_from = ip;
                 tab_w0 = tab_end = 0;
@@ -363,28 +379,44 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                 const uint32_t tag0 = lds_u8(stage_s + (ip & kStageMask));
                 if (lds_u8(lut_s + tag0) != 0) {   // a window that starts with a slow-path element is not worth a build
                     const uint32_t w0 = ip & ~3u;
-#pragma unroll 4
-                    for (int k = 0; k < kTabW / 128; k++) {
-                        const uint32_t wi = (uint32_t)lane + 32u * (uint32_t)k;
-                        const uint32_t pos = w0 + 4u * wi;
-                        const uint32_t word = lds_u32(stage_s + (pos & kStageMask));
-                        uint32_t st = lds_u8(lut_s + (word & 0xffu)) | (lds_u8(lut_s + ((word >> 8) & 0xffu)) << 8) |
-                                      (lds_u8(lut_s + ((word >> 16) & 0xffu)) << 16) | (lds_u8(lut_s + (word >> 24)) << 24);
-                        const int32_t nv = (int32_t)(in_end - pos);
-                        if (nv < 4) st = nv <= 0 ? 0u : (st & ((1u << (8 * nv)) - 1u));
-                        sts_u32(step_s + 4u * wi, st);
+                    // (volatile asm accessors execute in program order: batch the loads, then use them)
+                    {
+                        uint32_t word[kTabW / 128];
+#pragma unroll
+                        for (int k = 0; k < kTabW / 128; k++)
+                            word[k] = lds_u32(stage_s + ((w0 + 4u * ((uint32_t)lane + 32u * (uint32_t)k)) & kStageMask));
+#pragma unroll
+                        for (int h = 0; h < kTabW / 128; h += 2) {
+                            uint32_t e[8];
+#pragma unroll
+                            for (int q = 0; q < 8; q++)
+                                e[q] = lds_u8(lut_s + ((word[h + (q >> 2)] >> (8 * (q & 3))) & 0xffu));
+#pragma unroll
+                            for (int q = 0; q < 2; q++) {
+                                const uint32_t wi = (uint32_t)lane + 32u * (uint32_t)(h + q);
+                                uint32_t st = e[4 * q] | (e[4 * q + 1] << 8) | (e[4 * q + 2] << 16) | (e[4 * q + 3] << 24);
+                                const int32_t nv = (int32_t)(in_end - (w0 + 4u * wi));
+                                if (nv < 4) st = nv <= 0 ? 0u : (st & ((1u << (8 * nv)) - 1u));
+                                sts_u32(step_s + 4u * wi, st);
+                            }
+                        }
                     }
                     __syncwarp();
-#pragma unroll 4
-                    for (int k = 0; k < kTabW / 32; k++) {
-                        const uint32_t p0 = (uint32_t)lane + 32u * (uint32_t)k;
-                        const uint32_t s1 = lds_u8(step_s + p0);
-                        const uint32_t p1 = p0 + s1;
-                        const uint32_t s2 = lds_u8(step_s + p1);   // s1 == 0 re-reads the same 0: zeros propagate
-                        const uint32_t p2 = p1 + s2;
-                        const uint32_t s3 = lds_u8(step_s + p2);
-                        const uint32_t s4 = lds_u8(step_s + p2 + s3);
-                        sts_u32(quad_s + 4u * p0, s1 | (s2 << 8) | (s3 << 16) | (s4 << 24));
+#pragma unroll 1
+                    for (int k0 = 0; k0 < kTabW / 32; k0 += 8) {
+                        uint32_t s1[8], s2[8], s3[8], s4[8], pp[8];
+                        const uint32_t p0 = (uint32_t)lane + 32u * (uint32_t)k0;
+#pragma unroll
+                        for (int q = 0; q < 8; q++) s1[q] = lds_u8(step_s + p0 + 32u * q);
+#pragma unroll
+                        for (int q = 0; q < 8; q++) { pp[q] = p0 + 32u * q + s1[q]; s2[q] = lds_u8(step_s + pp[q]); }
+#pragma unroll
+                        for (int q = 0; q < 8; q++) { pp[q] += s2[q]; s3[q] = lds_u8(step_s + pp[q]); }   // zeros propagate:
+#pragma unroll
+                        for (int q = 0; q < 8; q++) { pp[q] += s3[q]; s4[q] = lds_u8(step_s + pp[q]); }   // a 0 re-reads itself
+#pragma unroll
+                        for (int q = 0; q < 8; q++)
+                            sts_u32(quad_s + 4u * (p0 + 32u * q), s1[q] | (s2[q] << 8) | (s3[q] << 16) | (s4[q] << 24));
                     }
                     __syncwarp();
                     tab_w0 = w0;
@@ -461,8 +493,8 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
             if (big) restart = true;
             __syncwarp();
             __threadfence_block();
-            placed[s]++;
-            named_bar_arrive(kBarFull + s, 64);
+            if (s == 0) owed0 = 1; else owed1 = 1;
+            named_bar_arrive<kBarFull, 2>(s);
             if (last) return;
         }
     } else {
@@ -482,7 +514,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
         };
         for (uint32_t b = 0;; b++) {
             const int s = b & 1;
-            named_bar_sync(kBarFull + s, 64);
+            named_bar_sync<kBarFull, 2>(s);
             const uint32_t bt_s = batches_s + (uint32_t)s * (uint32_t)sizeof(SnBatch);
             const uint4 hdr = lds_v4(bt_s + kHdrOff);
             const uint32_t n = hdr.x, last = hdr.y, perr = hdr.z, big_len = hdr.w;
@@ -616,7 +648,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                 }
                 return;
             }
-            named_bar_arrive(kBarEmpty + s, 64);
+            named_bar_arrive<kBarEmpty, 2>(s);
         }
     }
 }
@@ -691,48 +723,62 @@ k_snappy_index(const uint8_t *__restrict__ arena, const DevPage *__restrict__ pa
         const uint32_t tab_s = shared_addr(&tab[warp][0]), tmp_s = shared_addr(&tmp[warp][0]);
         const uint32_t lut_s = shared_addr(&lut[0]);
         for (uint32_t j = (uint32_t)warp; j < nwin; j += kIdxBuilders) {
-            if (j >= (uint32_t)kIdxBuilders) named_bar_sync(kBarIdxEmpty + warp, 64);
+            if (j >= (uint32_t)kIdxBuilders) named_bar_sync<kBarIdxEmpty, kIdxBuilders>(warp);
             const uint32_t w0 = j * kIdxW;
             const bool skip = __shfl_sync(0xffffffffu, (int)(give_up != 0 || w0 + kIdxW <= walker_ip), 0) != 0;
             if (!skip) {
+                // (the asm accessors are volatile, i.e. executed in program order: loads are issued in batches of
+                // eight before their results are used, otherwise every position would pay the full LDS latency)
                 // one element: every position as if a tag started there
-#pragma unroll 4
-                for (int k = 0; k < kIdxW / 128; k++) {
-                    const uint32_t wi = (uint32_t)lane + 32u * (uint32_t)k;
-                    const uint32_t pos = w0 + 4u * wi;
-                    uint32_t word = 0;
-                    if (pos < in_end16) word = __ldg(reinterpret_cast<const uint32_t *>(gin + pos));
-                    uint32_t e0 = lds_u32(lut_s + ((word & 0xffu) << 2));
-                    uint32_t e1 = lds_u32(lut_s + (((word >> 8) & 0xffu) << 2));
-                    uint32_t e2 = lds_u32(lut_s + (((word >> 16) & 0xffu) << 2));
-                    uint32_t e3 = lds_u32(lut_s + ((word >> 24) << 2));
-                    const int32_t nv = (int32_t)(in_end - pos);      // stream bytes in this word
-                    if (nv < 4) {
-                        if (nv < 1) e0 = 0;
-                        if (nv < 2) e1 = 0;
-                        if (nv < 3) e2 = 0;
-                        e3 = 0;
+                {
+                    uint32_t word[kIdxW / 128];
+#pragma unroll
+                    for (int k = 0; k < kIdxW / 128; k++) {
+                        const uint32_t pos = w0 + 4u * ((uint32_t)lane + 32u * (uint32_t)k);
+                        word[k] = pos < in_end16 ? __ldg(reinterpret_cast<const uint32_t *>(gin + pos)) : 0u;
                     }
-                    sts_v4(tab_s + 16u * wi, e0, e1, e2, e3);
+#pragma unroll
+                    for (int h = 0; h < kIdxW / 128; h += 2) {
+                        uint32_t e[8];
+#pragma unroll
+                        for (int q = 0; q < 8; q++)
+                            e[q] = lds_u32(lut_s + (((word[h + (q >> 2)] >> (8 * (q & 3))) & 0xffu) << 2));
+#pragma unroll
+                        for (int q = 0; q < 2; q++) {
+                            const uint32_t wi = (uint32_t)lane + 32u * (uint32_t)(h + q);
+                            const int32_t nv = (int32_t)(in_end - (w0 + 4u * wi));      // stream bytes in this word
+                            if (nv < 4) {
+                                if (nv < 1) e[4 * q] = 0;
+                                if (nv < 2) e[4 * q + 1] = 0;
+                                if (nv < 3) e[4 * q + 2] = 0;
+                                e[4 * q + 3] = 0;
+                            }
+                            sts_v4(tab_s + 16u * wi, e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]);
+                        }
+                    }
                 }
                 __syncwarp();
                 // 2, 4, 8, 16 elements by pointer doubling (the low half of an entry is already a byte offset)
                 uint32_t from_s = tab_s, to_s = tmp_s;
 #pragma unroll 1
                 for (int r = 0; r < 4; r++) {
-#pragma unroll 8
-                    for (int k = 0; k < kIdxW / 32; k++) {
-                        const uint32_t a0 = from_s + 4u * ((uint32_t)lane + 32u * (uint32_t)k);
-                        const uint32_t e = lds_u32(a0);
-                        const uint32_t f = lds_u32(a0 + (e & 0xffffu));     // e == 0 re-reads itself: stalls stay
-                        sts_u32(a0 - from_s + to_s, e + f);
+#pragma unroll 1
+                    for (int k0 = 0; k0 < kIdxW / 32; k0 += 8) {
+                        uint32_t e[8], f[8];
+                        const uint32_t a0 = from_s + 4u * ((uint32_t)lane + 32u * (uint32_t)k0);
+#pragma unroll
+                        for (int q = 0; q < 8; q++) e[q] = lds_u32(a0 + 128u * q);
+#pragma unroll
+                        for (int q = 0; q < 8; q++) f[q] = lds_u32(a0 + 128u * q + (e[q] & 0xffffu));   // e == 0 re-reads itself
+#pragma unroll
+                        for (int q = 0; q < 8; q++) sts_u32(a0 - from_s + to_s + 128u * q, e[q] + f[q]);
                     }
                     __syncwarp();
                     const uint32_t t = from_s; from_s = to_s; to_s = t;
                 }
             }
             __threadfence_block();
-            named_bar_arrive(kBarIdxFull + warp, 64);
+            named_bar_arrive<kBarIdxFull, kIdxBuilders>(warp);
         }
     } else {
         // ============================================ walker =====================================================
@@ -755,13 +801,26 @@ k_snappy_index(const uint8_t *__restrict__ arena, const DevPage *__restrict__ pa
         }
         for (uint32_t j = 0; j < nwin; j++) {
             const int b = (int)(j % kIdxBuilders);
-            named_bar_sync(kBarIdxFull + b, 64);
+            named_bar_sync<kBarIdxFull, kIdxBuilders>(b);
             const uint32_t wend = min((j + 1) * (uint32_t)kIdxW, in_end);
             if (lane == 0 && !flag && ip < wend) {
                 const uint32_t base = shared_addr(&tab[b][0]) - ((j * (uint32_t)kIdxW) << 2);
                 for (;;) {
-                    const uint32_t e = lds_u32(base + (ip << 2));
-                    const uint32_t adv = e & 0xffffu;
+                    // the chain: one LDS + two adds per 16 elements; forward exits only, one backward branch per 4 hops
+                    uint32_t a = base + (ip << 2), e, adv;
+                    for (;;) {
+                        bool out = false;
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            e = lds_u32(a);
+                            adv = e & 0xffffu;
+                            if (adv == 0 || op + (e >> 16) >= next_b) { out = true; break; }
+                            a += adv;
+                            op += e >> 16;
+                        }
+                        if (out) break;
+                    }
+                    ip = (a - base) >> 2;
                     if (adv == 0) {
                         if (ip >= wend) break;
                         // slow-path element: its length is in the stream, not in the tag
@@ -807,7 +866,7 @@ k_snappy_index(const uint8_t *__restrict__ arena, const DevPage *__restrict__ pa
             if (lane == 0) walker_ip = ip;
             if (j + kIdxBuilders < nwin) {
                 __threadfence_block();
-                named_bar_arrive(kBarIdxEmpty + b, 64);
+                named_bar_arrive<kBarIdxEmpty, kIdxBuilders>(b);
             }
         }
         if (lane == 0) {
@@ -1265,6 +1324,13 @@ k_decode_pages(uint8_t *__restrict__ arena, uint8_t *__restrict__ out, const Dev
 // launchers
 // ---------------------------------------------------------------------------------------------------------------
 cudaError_t configure_decode_kernels() {
+    // the Snappy kernels are latency-bound warps: as many CTAs per SM as their shared memory allows
+    cudaError_t e = cudaFuncSetAttribute(k_snappy_pages, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         (int)cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_snappy_index, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             (int)cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_decode_pages, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeShared));
 }
 

@@ -53,19 +53,14 @@ def _bits_for(level):
     return 0 if level == 0 else int(level).bit_length()
 
 
-def decode_plan(plan, native):
-    """Returns {slot: dict(values=..., valid=..., rep=..., defs=...)} decoded on the CPU from the raw image."""
+def read_tables(plan):
+    """(host copy of the raw region as uint8 array, DevCol tuples, DevPage tuples, arena offset of the page table)."""
     info = plan.info
     arena = np.zeros(info.arena_bytes, dtype=np.uint8)
     plan.fill_raw(arena.ctypes.data)
-    hp = plan.handle
-    # table offsets are not exported through the C-ABI; recover them from the layout rules (tables at the raw tail)
+    # table offsets are not exported through the C-ABI; recover them from the layout rules: cols at a 256-aligned
+    # tables_off behind the payloads, pages at align64(cols_end)
     ncols, npages = info.num_columns, info.num_pages
-    # scan backwards is fragile -> use the private symbol-free approach: tables_off is align256(max payload end).
-    # The planner guarantees cols at tables_off, pages at align64(cols_end).
-    ends = 0
-    pages = []
-    # find tables_off: smallest 256-aligned offset t such that DEVCOL/DEVPAGE parse consistently; we know page count
     for t in range(0, info.raw_bytes, 256):
         cols_end = t + DEVCOL.size * ncols
         pages_off = (cols_end + 63) // 64 * 64
@@ -86,6 +81,12 @@ def decode_plan(plan, native):
     cols = [DEVCOL.unpack_from(arena, tables_off + i * DEVCOL.size) for i in range(ncols)]
     pages_off = (tables_off + DEVCOL.size * ncols + 63) // 64 * 64
     pages = [DEVPAGE.unpack_from(arena, pages_off + i * DEVPAGE.size) for i in range(npages)]
+    return arena, cols, pages, pages_off
+
+
+def decode_plan(plan, native):
+    """Returns {slot: dict(values=..., valid=..., rep=..., defs=...)} decoded on the CPU from the raw image."""
+    arena, cols, pages, _ = read_tables(plan)
     result = {}
     images = {}
     for pi, pg in enumerate(pages):

@@ -198,3 +198,84 @@ def test_corrupt_page_is_reported(tmp_path):
     d = dec.decode_resident(plan, arena)
     with pytest.raises(rowgroup.DeviceDecodeError):
         d.check()
+
+
+def _varint(n):
+    out = bytearray()
+    while True:
+        b = n & 0x7f
+        n >>= 7
+        out.append(b | (0x80 if n else 0))
+        if not n:
+            return bytes(out)
+
+
+def _literals(data, chunk=60):
+    out = bytearray()
+    for i in range(0, len(data), chunk):
+        piece = data[i:i + chunk]
+        out.append((len(piece) - 1) << 2)
+        out += piece
+    return bytes(out)
+
+
+def _encode_periodic(img, period, head, wide_offsets):
+    """A valid raw-Snappy stream for `img` (periodic with `period` behind its first `head` bytes): literals for the
+    head, then 64-byte copies at distance `period` -- 4-byte offsets when `wide_offsets` (a distance the reference
+    compressor never produces), 2-byte offsets otherwise."""
+    out = bytearray(_varint(len(img)))
+    first = min(65536, head)
+    out += _literals(img[:first])                      # 1092 x 60 + 16: ends exactly on the 64 KiB boundary
+    out += _literals(img[first:head])
+    pos = head
+    while pos < len(img):
+        n = min(64, len(img) - pos)
+        if wide_offsets:
+            out.append(((n - 1) << 2) | 3)
+            out += period.to_bytes(4, 'little')
+        else:
+            out.append(((n - 1) << 2) | 2)
+            out += period.to_bytes(2, 'little')
+        pos += n
+    return bytes(out)
+
+
+@pytest.mark.parametrize('case', ['cross_fragment_copies', 'straddling_elements'])
+def test_snappy_streams_the_reference_compressor_never_emits(tmp_path, case):
+    """The parallel fragment decode relies on the 64 KiB block structure of snappy::RawCompress output.  Streams
+    without it are still valid Snappy: back-references that reach into an earlier 64 KiB block (found by the fragment
+    kernel, flag 2) and elements that straddle a block boundary (found by the index kernel, flag 1) must take the
+    serial fallback and decode to the same values."""
+    import torch
+    from petastorm_b200 import rowgroup
+    from plan_emulator import read_tables
+    n = 400000
+    period_values, head, wide = (10000, 80000, True) if case == 'cross_fragment_copies' else (4000, 32010, False)
+    vals = (np.arange(n, dtype=np.int64) % period_values) * 7919
+    schema = pa.schema([pa.field('a', pa.int64(), nullable=False)])
+    path = str(tmp_path / 'p.parquet')
+    pq.write_table(pa.table({'a': vals}, schema=schema), path, compression='snappy', use_dictionary=False,
+                   data_page_size=1 << 20)
+    dec = rowgroup.RowGroupDecoder()
+    plan = dec.plan(path, 0, [0])
+    host, _, pages, pages_off = read_tables(plan)
+    arena = dec.upload(plan, private=True)
+    torch.cuda.synchronize()
+    codec = pa.Codec('snappy')
+    patched = 0
+    for i, pg in enumerate(pages):
+        src_off, _, comp, uncomp = pg[0], pg[1], pg[2], pg[3]
+        if pg[11] != 1 or uncomp <= 2 * 65536:
+            continue
+        img = codec.decompress(bytes(host[src_off:src_off + comp]), decompressed_size=uncomp).to_pybytes()
+        stream = _encode_periodic(img, period_values * 8, head, wide)
+        assert codec.decompress(stream, decompressed_size=uncomp).to_pybytes() == img
+        assert len(stream) <= comp
+        arena[src_off:src_off + len(stream)] = torch.frombuffer(bytearray(stream), dtype=torch.uint8).to(arena.device)
+        size_field = torch.tensor([len(stream)], dtype=torch.int32).view(torch.uint8).to(arena.device)
+        arena[pages_off + i * 64 + 16:pages_off + i * 64 + 20] = size_field
+        patched += 1
+    assert patched >= 2
+    d = dec.decode_resident(plan, arena)
+    d.check()
+    np.testing.assert_array_equal(d.column(0).values.cpu().numpy(), vals)
