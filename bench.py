@@ -40,6 +40,11 @@ DATA_DIR = os.environ.get('PST_BENCH_DIR', '/tmp/pst_bench_c2')
 # ---------------------------------------------------------------------------------------------------------------------
 # synthetic data (np.random.default_rng(1234); float32 ~ N(0,1), int64 ~ U[0, 2^40))
 # ---------------------------------------------------------------------------------------------------------------------
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the C2 row-group, from the committed ncu --set full capture
+NCU_DRAM_SOURCE = 'profiles/r1_snappy_v8_fragments.txt (ncu --set full, one launch on a C2 row-group)'
+NCU_DRAM_BYTES_PER_LAUNCH = {'k_snappy_index': 93796608, 'k_snappy_pages': 543239424, 'k_decode_pages': 569219072}
+
+
 def _write_one(args):
     path, seed, rows = args
     import numpy as np
@@ -155,7 +160,7 @@ def cpu_reference_throughput(url, steps, warmup, workers):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=16)
+    ap.add_argument('--steps', type=int, default=64)
     ap.add_argument('--warmup', type=int, default=8)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--row-groups', type=int, default=8, help='row-groups materialised per GPU box (cycled)')
@@ -308,7 +313,8 @@ def main():
     algo_bytes = algo_by_kernel[dom]
     achieved = algo_bytes / (ms_avg[dom] / 1e3) / 1e9
     roofline = {'bound': 'hbm', 'kernel': names[dom], 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                'frac': achieved / peak, 'traffic': NCU_DRAM_BYTES_PER_LAUNCH.get(names[dom]), 'peak_source': peak_src,
+                'traffic_source': NCU_DRAM_SOURCE,
                 'algorithmic_bytes_per_launch': algo_bytes,
                 'kernel_ms': {n: float(m) for n, m in zip(names, ms_avg)},
                 'whole_decode_frac': (payload + rows_pg * ROW_BYTES) / (float(ms_avg.sum()) / 1e3) / 1e9 / peak}
