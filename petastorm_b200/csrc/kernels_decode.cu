@@ -1,6 +1,7 @@
 // sm_100a decode kernels for Parquet pages resident in HBM.
 //
-//   k_snappy_pages   K2  raw-Snappy block decompress, one CTA (4 warps) per page
+//   k_snappy_index   K2a compressed offset of every 64 KiB output boundary of a Snappy page (builder warps + walker)
+//   k_snappy_pages   K2  raw-Snappy decompress, one CTA (parser warp + executor warp) per 64 KiB fragment
 //   k_ba_dict_index  K4  BYTE_ARRAY dictionary entry index ({offset,len} per entry)
 //   k_decode_pages   K3/K4/K5/K6  levels (RLE/bit-packed hybrid) + PLAIN / dictionary values + validity,
 //                    one CTA (256 threads) per data page
@@ -11,7 +12,8 @@
 //
 // All of this is byte/integer work bound by HBM bandwidth, not by math: no tensor cores.  The design rules applied are
 // coalesced 16-byte accesses (the planner places every value section 16B-aligned, see host_api.cpp), shared-memory
-// staging of run tables, and one CTA per page so that a 256 MB row-group (~600 pages) fills the 148 SMs ~4x over.
+// staging of run tables, and work items small enough (64 KiB Snappy fragments, pages) that a 256 MB row-group
+// (~2900 pages, ~6300 fragments) fills the 148 SMs several times over.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -105,7 +107,8 @@ __device__ __forceinline__ void coop_fill(uint8_t *dst, uint8_t v, int64_t n, in
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K2  Snappy (raw block format, google/snappy format_description.txt).  One CTA = one page = two warps:
+// K2  Snappy (raw block format, google/snappy format_description.txt).  One CTA = one fragment (or, in the serial
+// fallback launch, one whole page) = two warps:
 //
 //   warp P (parser)    walks the element stream -- an inherently serial chain, every tag position depends on the
 //                      previous element -- with as few instructions per element as possible: tag bytes come from a
@@ -115,7 +118,7 @@ __device__ __forceinline__ void coop_fill(uint8_t *dst, uint8_t v, int64_t n, in
 //   warp X (executor)  takes one element per lane: a warp scan of the lengths gives every element its output
 //                      position, literal bytes go staging -> ring, back-references ring -> ring in dependency rounds
 //                      (a copy runs once every element in front of its source range is complete).  The ring holds the
-//                      most recent 32 KiB of output in shared memory, so the many tiny copies of a match-heavy stream
+//                      most recent 16 KiB of output in shared memory, so the many tiny copies of a match-heavy stream
 //                      never pay a global store -> L2 -> global load round trip; it is written through to HBM in
 //                      >= 4 KiB pieces with destination-aligned 16-byte stores.
 //
