@@ -132,7 +132,7 @@ __device__ __forceinline__ void coop_fill(uint8_t *dst, uint8_t v, int64_t n, in
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane);   // defined with the page decoder below
 
-constexpr int kSnappyThreads = 64;
+constexpr int kSnappyThreads = 96;      // parser warp, placement warp, copy warp
 constexpr int kRing = 16384;          // power of two; with the tables below ~30 KiB of shared memory per CTA (7 CTAs/SM)
 constexpr uint32_t kRingMask = kRing - 1;
 constexpr int kStage = 8192;          // input staging window: 4 chunks of 2 KiB (power of two)
@@ -231,8 +231,26 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
-constexpr int kBarFull = 1;    // +slot : P arrives, X syncs
-constexpr int kBarEmpty = 3;   // +slot : X arrives, P syncs
+constexpr int kBarFull = 1;    // +slot : P arrives, A syncs
+constexpr int kBarEmpty = 3;   // +slot : A arrives, P syncs
+constexpr int kBarExecFull = 5;    // +slot : A arrives, B syncs
+constexpr int kBarExecEmpty = 7;   // +slot : B arrives, A syncs
+// output bytes of one batch: 32 elements of <= 64 bytes plus a staged long literal (< kBigLiteral)
+constexpr uint32_t kMaxBatchOut = kBatchOps * 64 + kBigLiteral;
+
+struct SnExec {                 // warp A -> warp B: the back-references of one batch, positions already assigned
+    uint32_t d[kBatchOps];      // output position
+    uint32_t a[kBatchOps];      // distance to the source
+    uint32_t len[kBatchOps];    // 0 = this lane has no back-reference
+    uint32_t dst_end;           // output position behind the batch's elements
+    uint32_t big_len;           // bypassed literal that follows the batch (0 = none) ...
+    uint32_t big_src;           // ... and its input offset
+    uint32_t last;
+    uint32_t failed;
+    uint32_t pad_[3];
+};
+static_assert(sizeof(SnExec) == 416, "SnExec layout");
+constexpr uint32_t kExecHdr = kBatchOps * 12;
 
 __global__ void __launch_bounds__(kSnappyThreads)
 k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, const SnFrag *__restrict__ frags,
@@ -241,6 +259,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
     // one allocation: the vector copies may read up to 15 bytes past the end of the ring (into the padding)
     __shared__ __align__(16) uint8_t smem_all[kRing + 16 + kStage];
     __shared__ __align__(16) SnBatch batches[2];
+    __shared__ __align__(16) SnExec execs[2];
     __shared__ __align__(16) uint32_t quad_tab[kTabW + kTabPad];
     __shared__ __align__(16) uint8_t step_tab[kTabW + kTabPad];
     __shared__ __align__(16) uint8_t step_lut[256];
@@ -267,7 +286,8 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
         if (serial_mode ? flag == 0 : flag != 0) return;
     }
     const int lane = threadIdx.x & 31;
-    const bool is_parser = threadIdx.x < 32;
+    const int warp = threadIdx.x >> 5;
+    const bool is_parser = warp == 0;
 
     const uint8_t *src = arena + pg.src_off;
     uint8_t *dst = arena + pg.img_off;
@@ -288,7 +308,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
     // V2 data pages: the level bytes are stored uncompressed in front of the compressed values
     if (pg.kind == PK_DATA_V2) {
         uint32_t lv = (uint32_t)(pg.def_bytes + pg.rep_bytes);
-        if (!is_parser && frag_k == 0) coop_copy(dst, src, lv, lane, 32);
+        if (warp == 1 && frag_k == 0) coop_copy(dst, src, lv, lane, 32);
         src += lv; dst += lv; src_n -= lv; dst_n -= lv;
     }
     const uint32_t full_n = dst_n;            // the length the stream's preamble must announce
@@ -500,13 +520,130 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
             named_bar_arrive<kBarFull, 2>(s);
             if (last) return;
         }
-    } else {
-        // ============================================ warp X =====================================================
+    } else if (warp == 1) {
+        // ============================================ warp A =====================================================
+        // decodes the 32 elements of a batch (one per lane), assigns output positions with a warp scan, validates,
+        // moves the literal bytes staging -> ring and hands the back-references to warp B
         const uint32_t ring_s = shared_addr(ring), stage_s = shared_addr(stage), batches_s = shared_addr(&batches[0]);
+        const uint32_t execs_s = shared_addr(&execs[0]);
         uint32_t dst0 = 0;            // output position of the next batch
+        uint32_t owed0 = 0, owed1 = 0;
+        bool failed = false;
+        for (uint32_t b = 0;; b++) {
+            const int s = b & 1;
+            named_bar_sync<kBarFull, 2>(s);
+            const uint32_t bt_s = batches_s + (uint32_t)s * (uint32_t)sizeof(SnBatch);
+            const uint32_t ex_s = execs_s + (uint32_t)s * (uint32_t)sizeof(SnExec);
+            const uint4 hdr = lds_v4(bt_s + kHdrOff);
+            const uint32_t n = hdr.x, last = hdr.y, perr = hdr.z, big_len = hdr.w;
+            if (perr && !failed) {
+                failed = true;
+                if (lane == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, (int)perr);
+            }
+            // every lane decodes its own element from the staged bytes (the parser only located the hops): lane l
+            // takes element l & 3 of hop l >> 2; the slow-path element, if any, goes to the lane after the last hop
+            uint32_t kind = 0, a = 0, len = 0;
+            bool have = false, overrun = false;
+            const uint2 rare = lds_v2(bt_s + kHdrOff + 16);
+            if (!failed) {
+                const int h = lane >> 2, j = lane & 3;
+                if (h < (int)n) {
+                    const uint2 hp = lds_v2(bt_s + h * 8);
+                    if ((hp.y >> (8 * j)) & 0xffu) {
+                        const uint32_t pos = __dp4a(hp.y & ((1u << (8 * j)) - 1u), 0x01010101u, hp.x);
+                        const uint32_t tag = lds_u8(stage_s + (pos & kStageMask));
+                        const uint32_t b1 = lds_u8(stage_s + ((pos + 1) & kStageMask));
+                        const uint32_t b2 = lds_u8(stage_s + ((pos + 2) & kStageMask));
+                        const uint32_t t6 = tag >> 2;
+                        kind = tag & 3;
+                        have = true;
+                        overrun = pos + ((hp.y >> (8 * j)) & 0xffu) > in_end;
+                        if (kind == 0) { len = t6 + 1; a = pos + 1; }
+                        else if (kind == 1) { len = (t6 & 7) + 4; a = ((tag >> 5) << 8) | b1; }
+                        else { len = t6 + 1; a = b1 | (b2 << 8); kind = 1; }
+                    }
+                } else if (lane == 4 * (int)n && rare.y != 0) {
+                    a = rare.x;
+                    kind = rare.y >> 24;           // 1 copy-4, 2 bypassed big literal, 3 long staged literal
+                    len = kind == 2 ? 0u : (rare.y & 0xffffffu);
+                    if (kind == 3) kind = 0;
+                    have = true;
+                }
+            }
+            const uint32_t incl = warp_incl_scan(len, lane);
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t d = dst0 + incl - len;          // output position of this lane's element
+            const bool is_copy = have && kind == 1;
+            const bool has_big = !failed && (rare.y >> 24) == 2;
+            if (!failed) {
+                const bool cross = is_copy && a > d;      // source in front of this stream's first output byte
+                const bool bad = overrun || (d + len > dst_n) || (is_copy && a == 0) || (cross && frag_k == 0);
+                if (__any_sync(0xffffffffu, bad)) {
+                    failed = true;
+                    if (lane == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, 8);
+                } else if (__any_sync(0xffffffffu, cross)) {
+                    // a back-reference into an earlier fragment: legal Snappy, just not what the reference compressor
+                    // emits.  The page is handed to the serial fallback launch, which rewrites its whole image.
+                    failed = true;
+                    if (lane == 0) *(volatile uint32_t *)&page_flag[pg.multi_slot] = 2;
+                } else if (has_big && dst0 + total + big_len > dst_n) {
+                    failed = true;
+                    if (lane == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, 4);
+                } else if (last && dst0 + total + (has_big ? big_len : 0u) != dst_n) {
+                    failed = true;
+                    if (lane == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, 9);
+                }
+                if (failed) abort_flag = 1;
+            }
+            // the hand-over slot must be free BEFORE the ring is touched: that keeps this warp at most one batch ahead
+            // of warp B, which is what B's "source still in the ring" test assumes
+            if (s == 0) { if (owed0) { bar_sync_imm<kBarExecEmpty>(); owed0 = 0; } }
+            else if (owed1) { bar_sync_imm<kBarExecEmpty + 1>(); owed1 = 0; }
+            if (!failed) {
+                // ---- literals: staging -> ring.  Short ones per lane, longer ones by the whole warp.
+                const bool is_lit = have && kind == 0;
+                if (is_lit && len <= 16) {
+                    for (uint32_t i = 0; i < len; i++)
+                        sts_u8(ring_s + ((d + i) & kRingMask), lds_u8(stage_s + ((a + i) & kStageMask)));
+                }
+                uint32_t longs = __ballot_sync(0xffffffffu, is_lit && len > 16);
+                while (longs) {
+                    const int l = __ffs(longs) - 1;
+                    longs &= longs - 1;
+                    const uint32_t bl = __shfl_sync(0xffffffffu, len, l);
+                    const uint32_t bd = __shfl_sync(0xffffffffu, d, l);
+                    const uint32_t ba = __shfl_sync(0xffffffffu, a, l);
+                    for (uint32_t i = lane; i < bl; i += 32)
+                        sts_u8(ring_s + ((bd + i) & kRingMask), lds_u8(stage_s + ((ba + i) & kStageMask)));
+                }
+            }
+            sts_u32(ex_s + 4u * lane, d);
+            sts_u32(ex_s + 128u + 4u * lane, a);
+            sts_u32(ex_s + 256u + 4u * lane, (is_copy && !failed) ? len : 0u);
+            if (lane == 0) {
+                sts_v4(ex_s + kExecHdr, dst0 + total, has_big && !failed ? big_len : 0u, rare.x, last);
+                sts_u32(ex_s + kExecHdr + 16, failed ? 1u : 0u);
+            }
+            if (!failed) dst0 += total + (has_big ? big_len : 0u);
+            __syncwarp();
+            __threadfence_block();
+            if (s == 0) { bar_arrive_imm<kBarExecFull>(); owed0 = 1; }
+            else { bar_arrive_imm<kBarExecFull + 1>(); owed1 = 1; }
+            if (last) return;
+            named_bar_arrive<kBarEmpty, 2>(s);      // the staged bytes of this batch are no longer needed
+            if (has_big) {
+                // the bypassed literal moves the output position by an arbitrary amount, so the next batch's literals
+                // would land on ring slots warp B may still read: wait until B is done with this batch
+                if (s == 0) { bar_sync_imm<kBarExecEmpty>(); owed0 = 0; }
+                else { bar_sync_imm<kBarExecEmpty + 1>(); owed1 = 0; }
+            }
+        }
+    } else {
+        // ============================================ warp B =====================================================
+        // back-references ring -> ring in dependency rounds, write-through of the ring to HBM, bypassed literals
+        const uint32_t ring_s = shared_addr(ring), execs_s = shared_addr(&execs[0]);
         uint32_t flushed = 0;         // output bytes already written to global memory
         uint32_t valid_from = 0;      // output positions below this are not in the ring (bypassed literal)
-        bool failed = false;
         auto flush_to = [&](uint32_t t) {
             while (flushed < t) {
                 const uint32_t r = flushed & kRingMask;
@@ -517,141 +654,63 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
         };
         for (uint32_t b = 0;; b++) {
             const int s = b & 1;
-            named_bar_sync<kBarFull, 2>(s);
-            const uint32_t bt_s = batches_s + (uint32_t)s * (uint32_t)sizeof(SnBatch);
-            const uint4 hdr = lds_v4(bt_s + kHdrOff);
-            const uint32_t n = hdr.x, last = hdr.y, perr = hdr.z, big_len = hdr.w;
-            if (perr && !failed) {
-                failed = true;
-                if (lane == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, (int)perr);
-            }
+            named_bar_sync<kBarExecFull, 2>(s);
+            const uint32_t ex_s = execs_s + (uint32_t)s * (uint32_t)sizeof(SnExec);
+            const uint4 hdr = lds_v4(ex_s + kExecHdr);
+            const uint32_t dst_end = hdr.x, big_len = hdr.y, big_src = hdr.z, last = hdr.w;
+            const bool failed = lds_u32(ex_s + kExecHdr + 16) != 0;
             if (!failed) {
-                // every lane decodes its own element from the staged bytes (the parser only located the hops): lane l
-                // takes element l & 3 of hop l >> 2; the slow-path element, if any, goes to the lane after the last hop
-                uint32_t kind = 0, a = 0, len = 0;
-                bool have = false, overrun = false;
-                const uint2 rare = lds_v2(bt_s + kHdrOff + 16);
-                {
-                    const int h = lane >> 2, j = lane & 3;
-                    if (h < (int)n) {
-                        const uint2 hp = lds_v2(bt_s + h * 8);
-                        if ((hp.y >> (8 * j)) & 0xffu) {
-                            const uint32_t pos = __dp4a(hp.y & ((1u << (8 * j)) - 1u), 0x01010101u, hp.x);
-                            const uint32_t tag = lds_u8(stage_s + (pos & kStageMask));
-                            const uint32_t b1 = lds_u8(stage_s + ((pos + 1) & kStageMask));
-                            const uint32_t b2 = lds_u8(stage_s + ((pos + 2) & kStageMask));
-                            const uint32_t t6 = tag >> 2;
-                            kind = tag & 3;
-                            have = true;
-                            overrun = pos + ((hp.y >> (8 * j)) & 0xffu) > in_end;
-                            if (kind == 0) { len = t6 + 1; a = pos + 1; }
-                            else if (kind == 1) { len = (t6 & 7) + 4; a = ((tag >> 5) << 8) | b1; }
-                            else { len = t6 + 1; a = b1 | (b2 << 8); kind = 1; }
-                        }
-                    } else if (lane == 4 * (int)n && rare.y != 0) {
-                        a = rare.x;
-                        kind = rare.y >> 24;           // 1 copy-4, 2 bypassed big literal, 3 long staged literal
-                        len = kind == 2 ? 0u : (rare.y & 0xffffffu);
-                        if (kind == 3) kind = 0;
-                        have = true;
-                    }
-                }
-                const uint32_t incl = warp_incl_scan(len, lane);
-                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-                const uint32_t d = dst0 + incl - len;          // output position of this lane's element
-                const bool is_copy = have && kind == 1;
-                const bool cross = is_copy && a > d;      // source in front of this stream's first output byte
-                bool bad = overrun || (d + len > dst_n) || (is_copy && a == 0) || (cross && frag_k == 0);
-                if (__any_sync(0xffffffffu, bad)) {
-                    failed = true;
-                    abort_flag = 1;
-                    if (lane == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, 8);
-                } else if (__any_sync(0xffffffffu, cross)) {
-                    // a back-reference into an earlier fragment: legal Snappy, just not what the reference compressor
-                    // emits.  The page is handed to the serial fallback launch, which rewrites its whole image.
-                    failed = true;
-                    abort_flag = 1;
-                    if (lane == 0) *(volatile uint32_t *)&page_flag[pg.multi_slot] = 2;
-                } else {
-                    // ---- literals: staging -> ring.  Short ones per lane, longer ones by the whole warp.
-                    const bool is_lit = have && kind == 0;
-                    if (is_lit && len <= 16) {
-                        for (uint32_t i = 0; i < len; i++)
-                            sts_u8(ring_s + ((d + i) & kRingMask), lds_u8(stage_s + ((a + i) & kStageMask)));
-                    }
-                    uint32_t longs = __ballot_sync(0xffffffffu, is_lit && len > 16);
-                    while (longs) {
-                        const int l = __ffs(longs) - 1;
-                        longs &= longs - 1;
-                        const uint32_t bl = __shfl_sync(0xffffffffu, len, l);
-                        const uint32_t bd = __shfl_sync(0xffffffffu, d, l);
-                        const uint32_t ba = __shfl_sync(0xffffffffu, a, l);
-                        for (uint32_t i = lane; i < bl; i += 32)
-                            sts_u8(ring_s + ((bd + i) & kRingMask), lds_u8(stage_s + ((ba + i) & kStageMask)));
-                    }
-                    __syncwarp();
-                    // ---- back-references in dependency rounds
-                    const uint32_t sp = d - a;                                   // source position (copies only)
-                    const uint32_t src_end = min(sp + len, d);                   // bytes >= d are produced by the lane itself
-                    const bool in_ring = sp >= valid_from && (dst0 + total) - sp <= (uint32_t)kRing;
-                    uint32_t pending = __ballot_sync(0xffffffffu, is_copy);
-                    while (pending) {
-                        const int first = __ffs(pending) - 1;
-                        const uint32_t done_pos = __shfl_sync(0xffffffffu, d, first);   // everything below is complete
-                        const bool mine = (pending >> lane) & 1;
-                        bool ready = mine && (lane == first || src_end <= done_pos);
-                        if (ready && !in_ring && lane != first) ready = false;       // far sources wait for their turn
-                        const bool far_first = __shfl_sync(0xffffffffu, (int)(ready && !in_ring), first) != 0;
-                        if (far_first) {
-                            // the source left the ring (or was bypassed): complete output below done_pos goes to HBM first
-                            flush_to(done_pos);
-                            __syncwarp();
-                            if (lane == first) {
-                                for (uint32_t i = 0; i < len; i++) {
-                                    const uint32_t q = sp + i;
-                                    ring[(d + i) & kRingMask] = q < done_pos ? dst[q] : ring[q & kRingMask];
-                                }
+                const uint32_t d = lds_u32(ex_s + 4u * lane), a = lds_u32(ex_s + 128u + 4u * lane);
+                const uint32_t len = lds_u32(ex_s + 256u + 4u * lane);
+                const bool is_copy = len != 0;
+                const uint32_t sp = d - a;                                   // source position
+                const uint32_t src_end = min(sp + len, d);                   // bytes >= d are produced by the lane itself
+                // warp A may already be placing the literals of the next batch: the oldest kMaxBatchOut bytes of the
+                // ring are not trusted
+                const bool in_ring = sp >= valid_from && dst_end - sp <= (uint32_t)kRing - kMaxBatchOut;
+                uint32_t pending = __ballot_sync(0xffffffffu, is_copy);
+                while (pending) {
+                    const int first = __ffs(pending) - 1;
+                    const uint32_t done_pos = __shfl_sync(0xffffffffu, d, first);   // everything below is complete
+                    const bool mine = (pending >> lane) & 1;
+                    bool ready = mine && (lane == first || src_end <= done_pos);
+                    if (ready && !in_ring && lane != first) ready = false;       // far sources wait for their turn
+                    const bool far_first = __shfl_sync(0xffffffffu, (int)(ready && !in_ring), first) != 0;
+                    if (far_first) {
+                        // the source left the ring (or was bypassed): complete output below done_pos goes to HBM first
+                        flush_to(done_pos);
+                        __syncwarp();
+                        if (lane == first) {
+                            for (uint32_t i = 0; i < len; i++) {
+                                const uint32_t q = sp + i;
+                                ring[(d + i) & kRingMask] = q < done_pos ? dst[q] : ring[q & kRingMask];
                             }
                         }
-                        if (ready && in_ring) {
-                            // sequential per lane: an overlapping copy (offset < length) re-reads its own bytes
-                            for (uint32_t i = 0; i < len; i++)
-                                sts_u8(ring_s + ((d + i) & kRingMask), lds_u8(ring_s + ((d + i - a) & kRingMask)));
-                        }
-                        pending &= ~__ballot_sync(0xffffffffu, ready);
-                        __syncwarp();
                     }
-                    dst0 += total;
-                    // ---- bypassed big literal (always the last element of its batch)
-                    if ((rare.y >> 24) == 2) {
-                        const uint32_t bsrc = rare.x;
-                        if (dst0 + big_len > dst_n) {
-                            failed = true;
-                            abort_flag = 1;
-                            if (lane == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, 4);
-                        } else {
-                            flush_to(dst0);
-                            coop_copy(dst + dst0, gin + bsrc, big_len, lane, 32);
-                            dst0 += big_len;
-                            flushed = dst0;
-                            valid_from = dst0;
-                            __syncwarp();
-                        }
+                    if (ready && in_ring) {
+                        // sequential per lane: an overlapping copy (offset < length) re-reads its own bytes
+                        for (uint32_t i = 0; i < len; i++)
+                            sts_u8(ring_s + ((d + i) & kRingMask), lds_u8(ring_s + ((d + i - a) & kRingMask)));
                     }
-                    if (dst0 - flushed >= kFlushBytes) {
-                        flush_to(dst0);
-                        __syncwarp();
-                    }
+                    pending &= ~__ballot_sync(0xffffffffu, ready);
+                    __syncwarp();
+                }
+                uint32_t dst0 = dst_end;
+                if (big_len) {      // bypassed big literal (always behind the last element of its batch)
+                    flush_to(dst0);
+                    coop_copy(dst + dst0, gin + big_src, big_len, lane, 32);
+                    dst0 += big_len;
+                    flushed = dst0;
+                    valid_from = dst0;
+                    __syncwarp();
+                }
+                if (last || dst0 - flushed >= kFlushBytes) {
+                    flush_to(dst0);
+                    __syncwarp();
                 }
             }
-            if (last) {
-                if (!failed) {
-                    if (dst0 != dst_n) { if (lane == 0) report_error(status, DE_SNAPPY_CORRUPT, pi, 9); }
-                    else flush_to(dst0);
-                }
-                return;
-            }
-            named_bar_arrive<kBarEmpty, 2>(s);
+            if (last) return;
+            named_bar_arrive<kBarExecEmpty, 2>(s);
         }
     }
 }

@@ -7,6 +7,7 @@ Ownership rule: every decoded row-group owns its HBM (``arena`` = raw page bytes
 decoded columns) through ordinary torch tensors; column tensors handed to users are views that keep ``out`` alive, so
 nothing is recycled under the user (the reference never reuses output buffers either - SURVEY 8b).
 """
+import os
 import threading
 from ctypes import byref, c_int
 
@@ -175,7 +176,7 @@ class DecodedRowGroup(object):
 class RowGroupDecoder(object):
     """Issues plan -> upload -> decode for row-groups on side streams of one device."""
 
-    NUM_STREAMS = 5
+    NUM_STREAMS = int(os.environ.get('PST_DECODE_STREAMS', '5'))
 
     def __init__(self, device=None):
         self.ctx = get_context(device)
