@@ -41,8 +41,8 @@ DATA_DIR = os.environ.get('PST_BENCH_DIR', '/tmp/pst_bench_c2')
 # synthetic data (np.random.default_rng(1234); float32 ~ N(0,1), int64 ~ U[0, 2^40))
 # ---------------------------------------------------------------------------------------------------------------------
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the C2 row-group, from the committed ncu --set full capture
-NCU_DRAM_SOURCE = 'profiles/r1_snappy_v8_fragments.txt (ncu --set full, one launch on a C2 row-group)'
-NCU_DRAM_BYTES_PER_LAUNCH = {'k_snappy_index': 93796608, 'k_snappy_pages': 543239424, 'k_decode_pages': 569219072}
+NCU_DRAM_SOURCE = 'profiles/r1_final_three_stage.txt (ncu --set full, one launch on a C2 row-group)'
+NCU_DRAM_BYTES_PER_LAUNCH = {'k_snappy_index': 93603840, 'k_snappy_pages': 553425152, 'k_decode_pages': 570102272}
 
 
 def _write_one(args):

@@ -321,6 +321,11 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
         dst += (uint32_t)frag_k * (uint32_t)kSnappyFragment;
         dst_n = min((uint32_t)kSnappyFragment, full_n - (uint32_t)frag_k * (uint32_t)kSnappyFragment);
     }
+    // Output positions are biased by the misalignment of `dst`: position p lives at ring[p & mask] and at dst[p], so
+    // ring and HBM agree modulo 16 and the write-through is a plain 16-byte copy (no funnel shifts).
+    const uint32_t bias = (uint32_t)((uintptr_t)dst & 15);
+    dst -= bias;
+    dst_n += bias;
     __syncthreads();
     if ((int32_t)src_n <= 0) return;
 
@@ -526,7 +531,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
         // moves the literal bytes staging -> ring and hands the back-references to warp B
         const uint32_t ring_s = shared_addr(ring), stage_s = shared_addr(stage), batches_s = shared_addr(&batches[0]);
         const uint32_t execs_s = shared_addr(&execs[0]);
-        uint32_t dst0 = 0;            // output position of the next batch
+        uint32_t dst0 = bias;         // output position of the next batch
         uint32_t owed0 = 0, owed1 = 0;
         bool failed = false;
         for (uint32_t b = 0;; b++) {
@@ -576,7 +581,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
             const bool is_copy = have && kind == 1;
             const bool has_big = !failed && (rare.y >> 24) == 2;
             if (!failed) {
-                const bool cross = is_copy && a > d;      // source in front of this stream's first output byte
+                const bool cross = is_copy && a > d - bias;   // source in front of this stream's first output byte
                 const bool bad = overrun || (d + len > dst_n) || (is_copy && a == 0) || (cross && frag_k == 0);
                 if (__any_sync(0xffffffffu, bad)) {
                     failed = true;
@@ -642,8 +647,8 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
         // ============================================ warp B =====================================================
         // back-references ring -> ring in dependency rounds, write-through of the ring to HBM, bypassed literals
         const uint32_t ring_s = shared_addr(ring), execs_s = shared_addr(&execs[0]);
-        uint32_t flushed = 0;         // output bytes already written to global memory
-        uint32_t valid_from = 0;      // output positions below this are not in the ring (bypassed literal)
+        uint32_t flushed = bias;      // output positions below this are already in global memory
+        uint32_t valid_from = bias;      // output positions below this are not in the ring (bypassed literal)
         auto flush_to = [&](uint32_t t) {
             while (flushed < t) {
                 const uint32_t r = flushed & kRingMask;
