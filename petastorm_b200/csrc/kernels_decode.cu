@@ -133,7 +133,9 @@ __device__ __forceinline__ void coop_fill(uint8_t *dst, uint8_t v, int64_t n, in
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane);   // defined with the page decoder below
 
 constexpr int kSnappyThreads = 96;      // parser warp, placement warp, copy warp
-constexpr int kRing = 16384;          // power of two; with the tables below ~30 KiB of shared memory per CTA (7 CTAs/SM)
+constexpr int kRing = 16384;          // power of two; with staging and tables ~31 KiB of shared memory per CTA (7 CTAs/SM).
+// (8 KiB was measured: 9 CTAs/SM, but 8% of the back-references of the C2 int64 pages then reach behind the ring
+// and take the slow path through HBM -- 1.66 ms instead of 1.38 ms per row-group.)
 constexpr uint32_t kRingMask = kRing - 1;
 constexpr int kStage = 8192;          // input staging window: 4 chunks of 2 KiB (power of two)
 constexpr uint32_t kStageMask = kStage - 1;
@@ -143,7 +145,7 @@ constexpr int kBatchOps = 32;
 constexpr uint32_t kBatchIn = 2048;   // >= input span of a batch without its last element (32 elements x <= 62 bytes)
 // (output per batch is bounded by the two limits above: 32 copies x 64 B + < 2 KiB of literals)
 constexpr uint32_t kBigLiteral = 1024;
-constexpr uint32_t kFlushBytes = 4096;
+constexpr uint32_t kFlushBytes = 4096;   // kFlushBytes + 2 * kMaxBatchOut <= kRing: A never overwrites unflushed bytes
 constexpr uint32_t kLookahead = kBatchIn + kBigLiteral + 8;   // staged bytes a batch may touch past its start
 
 constexpr int kHops = kBatchOps / 4;   // the parser advances four elements per step ("hop")
@@ -231,10 +233,11 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
-constexpr int kBarFull = 1;    // +slot : P arrives, A syncs
-constexpr int kBarEmpty = 3;   // +slot : A arrives, P syncs
-constexpr int kBarExecFull = 5;    // +slot : A arrives, B syncs
-constexpr int kBarExecEmpty = 7;   // +slot : B arrives, A syncs
+// Hand-over between the stages is a RENDEZVOUS on one named barrier per pair of warps: when P and A meet, P has finished
+// writing batch b+1 and A has finished reading batch b (the slots are double-buffered), then both move on.  Two named
+// barriers per CTA (plus barrier 0) instead of eight keep the barrier file of the SM (64) from limiting residency.
+constexpr int kBarPA = 1;
+constexpr int kBarAB = 2;
 // output bytes of one batch: 32 elements of <= 64 bytes plus a staged long literal (< kBigLiteral)
 constexpr uint32_t kMaxBatchOut = kBatchOps * 64 + kBigLiteral;
 
@@ -359,15 +362,10 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
         uint32_t issued_end = ip & ~(kChunk - 1);   // input bytes below this have been requested
         uint32_t ready_end = issued_end;            // input bytes below this are resident in `stage`
         uint32_t keep_from = ip;                    // start of the previous batch: X may still read literals from there
-        uint32_t owed0 = 0, owed1 = 0;               // batches handed to X and not yet released, per slot (0 or 1)
         bool restart = false;
         for (uint32_t b = 0;; b++) {
             const int s = b & 1;
-            if (s == 0) { if (owed0) { bar_sync_imm<kBarEmpty>(); owed0 = 0; } }
-            else if (owed1) { bar_sync_imm<kBarEmpty + 1>(); owed1 = 0; }
-            if (restart) {   // after a bypassed literal the staging window moves: wait until X is done with everything
-                if (s == 1) { if (owed0) { bar_sync_imm<kBarEmpty>(); owed0 = 0; } }
-                else if (owed1) { bar_sync_imm<kBarEmpty + 1>(); owed1 = 0; }
+            if (restart) {   // after a bypassed literal the staging window moves (A is done with it: second rendezvous)
                 issued_end = ready_end = ip & ~(kChunk - 1);
                 keep_from = ip;
                 tab_w0 = tab_end = 0;
@@ -518,12 +516,14 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                 sts_v2(bt_s + kHdrOff + 16, rare_a, rare_h);
             }
             keep_from = batch_start;
-            if (big) restart = true;
             __syncwarp();
             __threadfence_block();
-            if (s == 0) owed0 = 1; else owed1 = 1;
-            named_bar_arrive<kBarFull, 2>(s);
+            bar_sync_imm<kBarPA>();                 // hand-over: A starts on this batch, its previous one is finished
             if (last) return;
+            if (big) {
+                bar_sync_imm<kBarPA>();             // A has moved this batch's literals out of the staging window
+                restart = true;
+            }
         }
     } else if (warp == 1) {
         // ============================================ warp A =====================================================
@@ -532,11 +532,10 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
         const uint32_t ring_s = shared_addr(ring), stage_s = shared_addr(stage), batches_s = shared_addr(&batches[0]);
         const uint32_t execs_s = shared_addr(&execs[0]);
         uint32_t dst0 = bias;         // output position of the next batch
-        uint32_t owed0 = 0, owed1 = 0;
         bool failed = false;
         for (uint32_t b = 0;; b++) {
             const int s = b & 1;
-            named_bar_sync<kBarFull, 2>(s);
+            bar_sync_imm<kBarPA>();
             const uint32_t bt_s = batches_s + (uint32_t)s * (uint32_t)sizeof(SnBatch);
             const uint32_t ex_s = execs_s + (uint32_t)s * (uint32_t)sizeof(SnExec);
             const uint4 hdr = lds_v4(bt_s + kHdrOff);
@@ -600,10 +599,8 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                 }
                 if (failed) abort_flag = 1;
             }
-            // the hand-over slot must be free BEFORE the ring is touched: that keeps this warp at most one batch ahead
-            // of warp B, which is what B's "source still in the ring" test assumes
-            if (s == 0) { if (owed0) { bar_sync_imm<kBarExecEmpty>(); owed0 = 0; } }
-            else if (owed1) { bar_sync_imm<kBarExecEmpty + 1>(); owed1 = 0; }
+            // (the rendezvous with B below keeps this warp exactly one batch ahead of B, which is what B's "source still in
+            // the ring" test assumes)
             if (!failed) {
                 // ---- literals: staging -> ring.  Short ones per lane, longer ones by the whole warp.
                 const bool is_lit = have && kind == 0;
@@ -632,15 +629,13 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
             if (!failed) dst0 += total + (has_big ? big_len : 0u);
             __syncwarp();
             __threadfence_block();
-            if (s == 0) { bar_arrive_imm<kBarExecFull>(); owed0 = 1; }
-            else { bar_arrive_imm<kBarExecFull + 1>(); owed1 = 1; }
+            if (big_len != 0 && !last) bar_sync_imm<kBarPA>();   // P may move the staging window now
+            bar_sync_imm<kBarAB>();                 // hand-over: B starts on this batch, its previous one is finished
             if (last) return;
-            named_bar_arrive<kBarEmpty, 2>(s);      // the staged bytes of this batch are no longer needed
-            if (has_big) {
+            if (has_big && !failed) {
                 // the bypassed literal moves the output position by an arbitrary amount, so the next batch's literals
                 // would land on ring slots warp B may still read: wait until B is done with this batch
-                if (s == 0) { bar_sync_imm<kBarExecEmpty>(); owed0 = 0; }
-                else { bar_sync_imm<kBarExecEmpty + 1>(); owed1 = 0; }
+                bar_sync_imm<kBarAB>();
             }
         }
     } else {
@@ -659,7 +654,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
         };
         for (uint32_t b = 0;; b++) {
             const int s = b & 1;
-            named_bar_sync<kBarExecFull, 2>(s);
+            bar_sync_imm<kBarAB>();
             const uint32_t ex_s = execs_s + (uint32_t)s * (uint32_t)sizeof(SnExec);
             const uint4 hdr = lds_v4(ex_s + kExecHdr);
             const uint32_t dst_end = hdr.x, big_len = hdr.y, big_src = hdr.z, last = hdr.w;
@@ -715,7 +710,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                 }
             }
             if (last) return;
-            named_bar_arrive<kBarExecEmpty, 2>(s);
+            if (big_len != 0 && !failed) bar_sync_imm<kBarAB>();   // tell A that the ring may be reused out of order
         }
     }
 }

@@ -71,7 +71,7 @@ def _is_data_file(name):
 class ParquetDataset(object):
     """A directory (or explicit list) of parquet files on the local filesystem."""
 
-    def __init__(self, path_or_paths):
+    def __init__(self, path_or_paths, filters=None):
         self.paths = path_or_paths
         self.pieces = []  # one per file: RowGroupPiece(path, None, partition_keys)
         self.partitions = PartitionSet()
@@ -101,6 +101,8 @@ class ParquetDataset(object):
                 self.pieces.append(RowGroupPiece(path_or_paths, None, []))
         self.pieces.sort(key=lambda p: p.path)
         self._finish_partitions()
+        if filters:
+            self.pieces = filter_pieces(self.pieces, filters)
         self._common_kv = None
         self._metadata_file = None
 
@@ -156,6 +158,51 @@ class ParquetDataset(object):
         if not self.pieces:
             raise IOError('No parquet files found in {}'.format(self.paths))
         return rowgroup.open_file(self.pieces[0].path)
+
+
+_FILTER_OPS = {
+    '=': lambda p, f: p == f, '==': lambda p, f: p == f, '!=': lambda p, f: p != f,
+    '<': lambda p, f: p < f, '>': lambda p, f: p > f, '<=': lambda p, f: p <= f, '>=': lambda p, f: p >= f,
+    'in': lambda p, f: p in f, 'not in': lambda p, f: p not in f,
+}
+
+
+def filter_pieces(pieces, filters):
+    """``filters`` of ``make_reader`` / ``make_batch_reader`` with the semantics the reference gets from the legacy
+    ``pq.ParquetDataset(filters=...)`` it builds (petastorm/reader.py:430-433): a list of ``(column, op, value)``
+    tuples (AND) or a list of such lists (OR of ANDs); only hive partition keys are tested - a predicate on any other
+    column accepts every file -, the partition value (a directory-name string) is cast to the type of the filter
+    value, and files whose partition keys fail every conjunction are dropped."""
+    if not isinstance(filters, (list, tuple)) or not filters:
+        raise ValueError('filters must be a non-empty List[Tuple] or List[List[Tuple]]')
+    dnf = [list(filters)] if isinstance(filters[0], tuple) or (isinstance(filters[0], list) and filters[0] and
+                                                                not isinstance(filters[0][0], (list, tuple))) \
+        else [list(c) for c in filters]
+    for conj in dnf:
+        for f in conj:
+            if len(f) != 3 or f[1] not in _FILTER_OPS:
+                raise ValueError('"{}" is not a valid filter: expected (column, op, value) with op in {}'.format(
+                    f, sorted(_FILTER_OPS)))
+            if f[1] in ('in', 'not in') and not isinstance(f[2], (set, list, tuple, frozenset)):
+                raise TypeError("'{}' object is not a collection".format(type(f[2]).__name__))
+
+    def accepts(piece, f):
+        column, op, value = f
+        for k, v in piece.partition_keys:
+            if k != column:
+                continue
+            if op in ('in', 'not in'):
+                values = list(value)
+                if not values:
+                    return op == 'not in'
+                cast = type(values[0])
+                if not _FILTER_OPS[op](cast(v), set(values)):
+                    return False
+            elif not _FILTER_OPS[op](type(value)(v), value):
+                return False
+        return True
+
+    return [p for p in pieces if any(all(accepts(p, f) for f in conj) for conj in dnf)]
 
 
 def _footer_split(piece):

@@ -171,15 +171,13 @@ class Reader(object):
                              'or an NGram object.')
         if output not in ('torch', 'numpy'):
             raise ValueError("output must be 'torch' or 'numpy'")
-        if filters:
-            raise NotImplementedError('pyarrow `filters` are not supported by the GPU reader yet; use a predicate')
         self.is_batched_reader = is_batched_reader
         # fail at construction (not at the first next()) when there is no CUDA device: no CPU fallback exists
         from petastorm_b200 import rowgroup
         rowgroup.get_context(device)
 
         # 1. open the dataset
-        self.dataset = dataset_metadata.ParquetDataset(dataset_path)
+        self.dataset = dataset_metadata.ParquetDataset(dataset_path, filters=filters)
         stored_schema = dataset_metadata.infer_or_load_unischema(self.dataset)
 
         if isinstance(schema_fields, NGram):

@@ -505,3 +505,26 @@ def test_shard_assignment_broadcast_gloo_world2(tmp_path):
     from petastorm_b200 import sharding
     assert sharding.shard_order(9, 2, 1) == [1, 3, 5, 7]
     assert sorted(sharding.shard_order(9, 2, 0, seed=3)) == [0, 2, 4, 6, 8]
+
+
+def test_partition_filters_follow_legacy_pyarrow_semantics(tmp_path):
+    """``filters`` prune FILES by hive partition key only (what the reference's legacy pq.ParquetDataset did,
+    petastorm/reader.py:430-433; reference tests test_end_to_end.py:917-937)."""
+    from petastorm_b200.etl import dataset_metadata as dm
+    url = datasets.write_flat(str(tmp_path / 'flat'), 300, files=3, row_group_size=40, partitioned=True)
+    path = url[7:]
+    parts = lambda ds: sorted({int(dict(p.partition_keys)['part']) for p in ds.pieces})
+    assert parts(dm.ParquetDataset(path)) == [0, 1, 2]
+    assert parts(dm.ParquetDataset(path, filters=[('part', '=', 1)])) == [1]
+    assert parts(dm.ParquetDataset(path, filters=[('part', '!=', 1)])) == [0, 2]
+    assert parts(dm.ParquetDataset(path, filters=[('part', '>=', 1), ('part', '<', 2)])) == [1]
+    assert parts(dm.ParquetDataset(path, filters=[[('part', '=', 0)], [('part', '=', 2)]])) == [0, 2]
+    assert parts(dm.ParquetDataset(path, filters=[('part', 'in', {0, 2})])) == [0, 2]
+    assert parts(dm.ParquetDataset(path, filters=[('part', 'not in', [0])])) == [1, 2]
+    assert parts(dm.ParquetDataset(path, filters=[('part', '=', '2')])) == [2]          # value type decides the cast
+    assert parts(dm.ParquetDataset(path, filters=[('f0', '>', 1e9)])) == [0, 1, 2]      # not a partition key: ignored
+    assert parts(dm.ParquetDataset(path, filters=[('part', '=', 7)])) == []
+    with pytest.raises(ValueError):
+        dm.ParquetDataset(path, filters=[('part', '~', 1)])
+    with pytest.raises(TypeError):
+        dm.ParquetDataset(path, filters=[('part', 'in', 1)])
