@@ -235,6 +235,11 @@ static int launch_snappy_stage(pst_plan *p, uint8_t *arena, int32_t *status, cud
            "snappy fallback launch");
         nl++;
     }
+    if (!p->gzip_pages.empty()) {   // (timed together with the Snappy fallback slot: a plan normally has one codec)
+        ck(launch_gzip_pages(arena, pages, (const int32_t *)(arena + p->gzip_list_off), (int)p->gzip_pages.size(),
+                             status, s), "gzip launch");
+        nl++;
+    }
     if (ev) ck(cudaEventRecord(ev[3], s), "record");
     return nl;
 }

@@ -17,7 +17,7 @@ enum Enc : uint8_t {
 enum DevErr : int32_t {
     DE_OK = 0, DE_SNAPPY_CORRUPT = 1, DE_LEVELS_CORRUPT = 2, DE_UNSUPPORTED_ENCODING = 3, DE_DICT_INDEX_RANGE = 4,
     DE_PAGE_OVERRUN = 5, DE_NPY_HEADER_MISMATCH = 6, DE_PNG_CORRUPT = 7, DE_PNG_UNSUPPORTED = 8,
-    DE_NGRAM_UNSORTED = 9, DE_BYTE_ARRAY_CORRUPT = 10
+    DE_NGRAM_UNSORTED = 9, DE_BYTE_ARRAY_CORRUPT = 10, DE_GZIP_CORRUPT = 11
 };
 
 constexpr int32_t kSnappyFragment = 65536;
@@ -39,7 +39,7 @@ struct DevPage {            // 64 bytes
     int16_t col;            // plan column slot
     uint8_t kind;           // PageKind
     uint8_t encoding;       // Enc of the values
-    uint8_t codec;          // 0 none, 1 snappy
+    uint8_t codec;          // 0 none, 1 snappy, 2 gzip
     uint8_t def_enc;        // V1: Enc of definition levels
     uint8_t rep_enc;        // V1: Enc of repetition levels
     uint8_t v2_compressed;  // V2: values section compressed?

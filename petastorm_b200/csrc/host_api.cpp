@@ -280,9 +280,9 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
         const LeafColumn &leaf = f->meta.leaves[col];
         const SchemaElement &se = f->meta.schema[leaf.schema_index];
         if (!c.file_path.empty()) throw std::runtime_error("column chunks stored in external files are not supported");
-        if (c.codec != PST_CODEC_NONE && c.codec != PST_CODEC_SNAPPY)
+        if (c.codec != PST_CODEC_NONE && c.codec != PST_CODEC_SNAPPY && c.codec != PST_CODEC_GZIP)
             throw std::runtime_error("unsupported compression codec " + std::to_string(c.codec) +
-                                     " (supported: UNCOMPRESSED, SNAPPY) in column " + se.name);
+                                     " (supported: UNCOMPRESSED, SNAPPY, GZIP) in column " + se.name);
         DevCol &dc = p->dcols[slot];
         memset(&dc, 0, sizeof dc);
         dc.ptype = c.type;
@@ -381,18 +381,23 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
                 int64_t rel = align_up(scratch_cur, 16) + phase;
                 scratch_rel.push_back(rel);
                 scratch_cur = rel + d.uncomp_size + 16;  // +16: vector-store slack
-                p->compressed_pages.push_back((int32_t)p->pages.size());
-                // the compressed stream covers the whole image (V1) or everything behind the level bytes (V2)
-                const int64_t values_uncomp = (int64_t)d.uncomp_size -
-                                              (d.kind == PK_DATA_V2 ? (int64_t)d.def_bytes + d.rep_bytes : 0);
-                d.nfrag = (int32_t)std::max<int64_t>(1, (values_uncomp + kSnappyFragment - 1) / kSnappyFragment);
-                d.frag_first = (int32_t)p->frag_pos_count;
-                p->frag_pos_count += d.nfrag + 1;
-                if (d.nfrag > 1) {
-                    d.multi_slot = (int32_t)p->multi_pages.size();
-                    p->multi_pages.push_back((int32_t)p->pages.size());
+                if (d.codec == PST_CODEC_GZIP) {
+                    p->gzip_pages.push_back((int32_t)p->pages.size());
+                } else {
+                    p->compressed_pages.push_back((int32_t)p->pages.size());
+                    // the compressed stream covers the whole image (V1) or everything behind the level bytes (V2)
+                    const int64_t values_uncomp = (int64_t)d.uncomp_size -
+                                                  (d.kind == PK_DATA_V2 ? (int64_t)d.def_bytes + d.rep_bytes : 0);
+                    d.nfrag = (int32_t)std::max<int64_t>(1, (values_uncomp + kSnappyFragment - 1) / kSnappyFragment);
+                    d.frag_first = (int32_t)p->frag_pos_count;
+                    p->frag_pos_count += d.nfrag + 1;
+                    if (d.nfrag > 1) {
+                        d.multi_slot = (int32_t)p->multi_pages.size();
+                        p->multi_pages.push_back((int32_t)p->pages.size());
+                    }
+                    for (int32_t k = 0; k < d.nfrag; k++)
+                        p->snappy_frags.push_back(SnFrag{(int32_t)p->pages.size(), k});
                 }
-                for (int32_t k = 0; k < d.nfrag; k++) p->snappy_frags.push_back(SnFrag{(int32_t)p->pages.size(), k});
             } else {
                 d.src_off = align_up(raw_cur, 16) + phase;
                 raw_cur = d.src_off + d.comp_size + 16;  // +16: vector-load slack
@@ -436,7 +441,8 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
     p->dict_list_off = align_up(p->data_list_off + 4 * (int64_t)p->data_pages.size(), 16);
     p->frag_list_off = align_up(p->dict_list_off + 4 * (int64_t)p->ba_dict_pages.size(), 16);
     p->multi_list_off = align_up(p->frag_list_off + (int64_t)sizeof(SnFrag) * (int64_t)p->snappy_frags.size(), 16);
-    p->raw_bytes = align_up(p->multi_list_off + 4 * (int64_t)p->multi_pages.size(), 256);
+    p->gzip_list_off = align_up(p->multi_list_off + 4 * (int64_t)p->multi_pages.size(), 16);
+    p->raw_bytes = align_up(p->gzip_list_off + 4 * (int64_t)p->gzip_pages.size(), 256);
     p->scratch_off = p->raw_bytes;
     {   // device-written tables of the Snappy fragment index (behind the page images)
         int64_t rel = align_up(scratch_cur, 16);
@@ -499,6 +505,8 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
         memcpy(t + (p->frag_list_off - p->tables_off), p->snappy_frags.data(), sizeof(SnFrag) * p->snappy_frags.size());
     if (!p->multi_pages.empty())
         memcpy(t + (p->multi_list_off - p->tables_off), p->multi_pages.data(), 4 * p->multi_pages.size());
+    if (!p->gzip_pages.empty())
+        memcpy(t + (p->gzip_list_off - p->tables_off), p->gzip_pages.data(), 4 * p->gzip_pages.size());
 
     // cache key: file identity + row group + column set
     uint64_t key = 1469598103934665603ull;
@@ -531,7 +539,7 @@ int pst_plan_get_info(const pst_plan *p, pst_plan_info *out) {
     out->uncompressed_bytes = p->uncompressed_bytes;
     out->num_pages = (int32_t)p->pages.size();
     out->num_columns = (int32_t)p->cols.size();
-    out->num_compressed_pages = (int32_t)p->compressed_pages.size();
+    out->num_compressed_pages = (int32_t)(p->compressed_pages.size() + p->gzip_pages.size());
     out->reserved = 0;
     return 0;
 }

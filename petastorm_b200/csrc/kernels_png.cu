@@ -162,6 +162,123 @@ __device__ __forceinline__ int paeth(int a, int b, int c) {
     return c;
 }
 
+// DEFLATE blocks (RFC 1951) from the bit reader into raw[op ..), at most raw_total bytes; returns 0 or 1 (corrupt).
+// One lane; `ws` holds the Huffman tables of its warp.
+__device__ int deflate_blocks(Bits &b, Src &s, uint8_t *raw, int64_t raw_total, WarpState &ws, int64_t &op) {
+    int err = 0;
+    int last = 0;
+    while (!err && !last) {
+        last = bits_get(b, s, 1);
+        int type = bits_get(b, s, 2);
+        if (last < 0 || type < 0) { err = 1; break; }
+        if (type == 0) {
+            // stored: drop bits to the byte boundary, LEN / NLEN, then raw bytes
+            b.buf = 0;
+            b.cnt = 0;  // bits_get refills byte-wise, so a partial byte is all that can be buffered... see note
+            int l0 = src_byte(s), l1 = src_byte(s), n0 = src_byte(s), n1 = src_byte(s);
+            if (l0 < 0 || l1 < 0 || n0 < 0 || n1 < 0) { err = 1; break; }
+            int len = l0 | (l1 << 8);
+            if ((len ^ 0xffff) != (n0 | (n1 << 8))) { err = 1; break; }
+            if (op + len > raw_total) { err = 1; break; }
+            while (len > 0) {
+                if (s.p == s.seg_end) {
+                    src_next_segment(s);
+                    if (s.eof) { err = 1; break; }
+                }
+                int64_t take = s.seg_end - s.p;
+                if (take > len) take = len;
+                for (int64_t i = 0; i < take; i++) raw[op + i] = s.p[i];
+                s.p += take;
+                op += take;
+                len -= (int)take;
+            }
+            continue;
+        }
+        if (type == 3) { err = 1; break; }
+        if (type == 1) {
+            int sym = 0;
+            for (; sym < 144; sym++) ws.lengths[sym] = 8;
+            for (; sym < 256; sym++) ws.lengths[sym] = 9;
+            for (; sym < 280; sym++) ws.lengths[sym] = 7;
+            for (; sym < kFixLCodes; sym++) ws.lengths[sym] = 8;
+            huff_build(ws.lencode, ws.lengths, kFixLCodes);
+            for (sym = 0; sym < kMaxDCodes; sym++) ws.lengths[sym] = 5;
+            huff_build(ws.distcode, ws.lengths, kMaxDCodes);
+        } else {
+            int nlen = bits_get(b, s, 5), ndist = bits_get(b, s, 5), ncode = bits_get(b, s, 4);
+            if (nlen < 0 || ndist < 0 || ncode < 0) { err = 1; break; }
+            nlen += 257; ndist += 1; ncode += 4;
+            if (nlen > kMaxLCodes || ndist > kMaxDCodes) { err = 1; break; }
+            int idx = 0;
+            for (; idx < ncode; idx++) {
+                int v = bits_get(b, s, 3);
+                if (v < 0) { err = 1; break; }
+                ws.lengths[c_clen_order[idx]] = (uint16_t)v;
+            }
+            if (err) break;
+            for (; idx < 19; idx++) ws.lengths[c_clen_order[idx]] = 0;
+            if (huff_build(ws.lencode, ws.lengths, 19) != 0) { err = 1; break; }
+            idx = 0;
+            while (idx < nlen + ndist) {
+                int sym = huff_decode(b, s, ws.lencode);
+                if (sym < 0) { err = 1; break; }
+                if (sym < 16) ws.lengths[idx++] = (uint16_t)sym;
+                else {
+                    int len = 0, rep;
+                    if (sym == 16) {
+                        if (idx == 0) { err = 1; break; }
+                        len = ws.lengths[idx - 1];
+                        rep = bits_get(b, s, 2);
+                        if (rep < 0) { err = 1; break; }
+                        rep += 3;
+                    } else if (sym == 17) {
+                        rep = bits_get(b, s, 3);
+                        if (rep < 0) { err = 1; break; }
+                        rep += 3;
+                    } else {
+                        rep = bits_get(b, s, 7);
+                        if (rep < 0) { err = 1; break; }
+                        rep += 11;
+                    }
+                    if (idx + rep > nlen + ndist) { err = 1; break; }
+                    while (rep--) ws.lengths[idx++] = (uint16_t)len;
+                }
+            }
+            if (err) break;
+            if (ws.lengths[256] == 0) { err = 1; break; }
+            int e1 = huff_build(ws.lencode, ws.lengths, nlen);
+            if (e1 < 0 || (e1 > 0 && nlen - ws.lencode.count[0] != 1)) { err = 1; break; }
+            int e2 = huff_build(ws.distcode, ws.lengths + nlen, ndist);
+            if (e2 < 0 || (e2 > 0 && ndist - ws.distcode.count[0] != 1)) { err = 1; break; }
+        }
+        // literal/length + distance codes
+        for (;;) {
+            int sym = huff_decode(b, s, ws.lencode);
+            if (sym < 0) { err = 1; break; }
+            if (sym < 256) {
+                if (op >= raw_total) { err = 1; break; }
+                raw[op++] = (uint8_t)sym;
+            } else if (sym == 256) {
+                break;
+            } else {
+                sym -= 257;
+                if (sym >= 29) { err = 1; break; }
+                int eb = bits_get(b, s, c_len_extra[sym]);
+                if (eb < 0) { err = 1; break; }
+                int len = c_len_base[sym] + eb;
+                int ds = huff_decode(b, s, ws.distcode);
+                if (ds < 0 || ds >= 30) { err = 1; break; }
+                int de = bits_get(b, s, c_dist_extra[ds]);
+                if (de < 0) { err = 1; break; }
+                int64_t dist = (int64_t)c_dist_base[ds] + de;
+                if (dist > op || op + len > raw_total) { err = 1; break; }
+                for (int i = 0; i < len; i++, op++) raw[op] = raw[op - dist];
+            }
+        }
+    }
+    return err;
+}
+
 constexpr int kPngWarpsPerBlock = 2;
 
 __global__ void __launch_bounds__(32 * kPngWarpsPerBlock)
@@ -251,116 +368,7 @@ k_png_batch(const uint8_t *__restrict__ base, const int64_t *__restrict__ offs, 
             int cmf = bits_get(b, s, 8), flg = bits_get(b, s, 8);
             if (cmf < 0 || flg < 0 || (cmf & 15) != 8 || ((cmf << 8) + flg) % 31 != 0 || (flg & 0x20)) err = DE_PNG_CORRUPT;
             int64_t op = 0;
-            int last = 0;
-            while (!err && !last) {
-                last = bits_get(b, s, 1);
-                int type = bits_get(b, s, 2);
-                if (last < 0 || type < 0) { err = DE_PNG_CORRUPT; break; }
-                if (type == 0) {
-                    // stored: drop bits to the byte boundary, LEN / NLEN, then raw bytes
-                    b.buf = 0;
-                    b.cnt = 0;  // bits_get refills byte-wise, so a partial byte is all that can be buffered... see note
-                    int l0 = src_byte(s), l1 = src_byte(s), n0 = src_byte(s), n1 = src_byte(s);
-                    if (l0 < 0 || l1 < 0 || n0 < 0 || n1 < 0) { err = DE_PNG_CORRUPT; break; }
-                    int len = l0 | (l1 << 8);
-                    if ((len ^ 0xffff) != (n0 | (n1 << 8))) { err = DE_PNG_CORRUPT; break; }
-                    if (op + len > raw_total) { err = DE_PNG_CORRUPT; break; }
-                    while (len > 0) {
-                        if (s.p == s.seg_end) {
-                            src_next_segment(s);
-                            if (s.eof) { err = DE_PNG_CORRUPT; break; }
-                        }
-                        int64_t take = s.seg_end - s.p;
-                        if (take > len) take = len;
-                        for (int64_t i = 0; i < take; i++) raw[op + i] = s.p[i];
-                        s.p += take;
-                        op += take;
-                        len -= (int)take;
-                    }
-                    continue;
-                }
-                if (type == 3) { err = DE_PNG_CORRUPT; break; }
-                if (type == 1) {
-                    int sym = 0;
-                    for (; sym < 144; sym++) ws.lengths[sym] = 8;
-                    for (; sym < 256; sym++) ws.lengths[sym] = 9;
-                    for (; sym < 280; sym++) ws.lengths[sym] = 7;
-                    for (; sym < kFixLCodes; sym++) ws.lengths[sym] = 8;
-                    huff_build(ws.lencode, ws.lengths, kFixLCodes);
-                    for (sym = 0; sym < kMaxDCodes; sym++) ws.lengths[sym] = 5;
-                    huff_build(ws.distcode, ws.lengths, kMaxDCodes);
-                } else {
-                    int nlen = bits_get(b, s, 5), ndist = bits_get(b, s, 5), ncode = bits_get(b, s, 4);
-                    if (nlen < 0 || ndist < 0 || ncode < 0) { err = DE_PNG_CORRUPT; break; }
-                    nlen += 257; ndist += 1; ncode += 4;
-                    if (nlen > kMaxLCodes || ndist > kMaxDCodes) { err = DE_PNG_CORRUPT; break; }
-                    int idx = 0;
-                    for (; idx < ncode; idx++) {
-                        int v = bits_get(b, s, 3);
-                        if (v < 0) { err = DE_PNG_CORRUPT; break; }
-                        ws.lengths[c_clen_order[idx]] = (uint16_t)v;
-                    }
-                    if (err) break;
-                    for (; idx < 19; idx++) ws.lengths[c_clen_order[idx]] = 0;
-                    if (huff_build(ws.lencode, ws.lengths, 19) != 0) { err = DE_PNG_CORRUPT; break; }
-                    idx = 0;
-                    while (idx < nlen + ndist) {
-                        int sym = huff_decode(b, s, ws.lencode);
-                        if (sym < 0) { err = DE_PNG_CORRUPT; break; }
-                        if (sym < 16) ws.lengths[idx++] = (uint16_t)sym;
-                        else {
-                            int len = 0, rep;
-                            if (sym == 16) {
-                                if (idx == 0) { err = DE_PNG_CORRUPT; break; }
-                                len = ws.lengths[idx - 1];
-                                rep = bits_get(b, s, 2);
-                                if (rep < 0) { err = DE_PNG_CORRUPT; break; }
-                                rep += 3;
-                            } else if (sym == 17) {
-                                rep = bits_get(b, s, 3);
-                                if (rep < 0) { err = DE_PNG_CORRUPT; break; }
-                                rep += 3;
-                            } else {
-                                rep = bits_get(b, s, 7);
-                                if (rep < 0) { err = DE_PNG_CORRUPT; break; }
-                                rep += 11;
-                            }
-                            if (idx + rep > nlen + ndist) { err = DE_PNG_CORRUPT; break; }
-                            while (rep--) ws.lengths[idx++] = (uint16_t)len;
-                        }
-                    }
-                    if (err) break;
-                    if (ws.lengths[256] == 0) { err = DE_PNG_CORRUPT; break; }
-                    int e1 = huff_build(ws.lencode, ws.lengths, nlen);
-                    if (e1 < 0 || (e1 > 0 && nlen - ws.lencode.count[0] != 1)) { err = DE_PNG_CORRUPT; break; }
-                    int e2 = huff_build(ws.distcode, ws.lengths + nlen, ndist);
-                    if (e2 < 0 || (e2 > 0 && ndist - ws.distcode.count[0] != 1)) { err = DE_PNG_CORRUPT; break; }
-                }
-                // literal/length + distance codes
-                for (;;) {
-                    int sym = huff_decode(b, s, ws.lencode);
-                    if (sym < 0) { err = DE_PNG_CORRUPT; break; }
-                    if (sym < 256) {
-                        if (op >= raw_total) { err = DE_PNG_CORRUPT; break; }
-                        raw[op++] = (uint8_t)sym;
-                    } else if (sym == 256) {
-                        break;
-                    } else {
-                        sym -= 257;
-                        if (sym >= 29) { err = DE_PNG_CORRUPT; break; }
-                        int eb = bits_get(b, s, c_len_extra[sym]);
-                        if (eb < 0) { err = DE_PNG_CORRUPT; break; }
-                        int len = c_len_base[sym] + eb;
-                        int ds = huff_decode(b, s, ws.distcode);
-                        if (ds < 0 || ds >= 30) { err = DE_PNG_CORRUPT; break; }
-                        int de = bits_get(b, s, c_dist_extra[ds]);
-                        if (de < 0) { err = DE_PNG_CORRUPT; break; }
-                        int64_t dist = (int64_t)c_dist_base[ds] + de;
-                        if (dist > op || op + len > raw_total) { err = DE_PNG_CORRUPT; break; }
-                        for (int i = 0; i < len; i++, op++) raw[op] = raw[op - dist];
-                    }
-                }
-            }
+            if (!err && deflate_blocks(b, s, raw, raw_total, ws, op)) err = DE_PNG_CORRUPT;
             if (!err && op != raw_total) err = DE_PNG_CORRUPT;
             ws.err = err;
         }
@@ -448,6 +456,73 @@ k_png_batch(const uint8_t *__restrict__ base, const int64_t *__restrict__ offs, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Parquet pages compressed with GZIP (RFC 1952 members around a DEFLATE stream): one warp per page, lane 0 inflates
+// into the page image in the arena scratch, the other lanes only move the uncompressed level bytes of V2 pages.
+// Replaces the gzip decompression inside Arrow C++ `piece.read` (petastorm/arrow_reader_worker.py:358).  The bit
+// stream is serial, so the parallelism is the number of pages of the row-group.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * kPngWarpsPerBlock)
+k_gzip_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, const int32_t *__restrict__ list, int n_list,
+             int32_t *status) {
+    __shared__ WarpState wstate[kPngWarpsPerBlock];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpState &ws = wstate[warp];
+    const int li = blockIdx.x * kPngWarpsPerBlock + warp;
+    if (li >= n_list) return;
+    const int pi = list[li];
+    const DevPage pg = pages[pi];
+    const uint8_t *src = arena + pg.src_off;
+    uint8_t *dst = arena + pg.img_off;
+    int64_t src_n = pg.comp_size, dst_n = pg.uncomp_size;
+    if (pg.kind == PK_DATA_V2) {
+        const int64_t lv = (int64_t)pg.def_bytes + pg.rep_bytes;
+        for (int64_t i = lane; i < lv; i += 32) dst[i] = src[i];
+        src += lv; dst += lv; src_n -= lv; dst_n -= lv;
+    }
+    if (lane != 0 || src_n <= 0) return;
+    Src s;
+    s.p = src;
+    s.seg_end = s.blob_end = src + src_n;
+    s.eof = true;                       // a single segment: the reader never looks for a next one
+    int err = 0;
+    int64_t op = 0;
+    while (!err && op < dst_n) {        // members may be concatenated
+        if (s.seg_end - s.p < 18) { err = 1; break; }
+        const uint8_t *h = s.p;
+        const int flg = h[3];
+        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || (flg & 0xe0)) { err = 2; break; }
+        s.p += 10;
+        if (flg & 4) {                  // FEXTRA
+            if (s.seg_end - s.p < 2) { err = 1; break; }
+            const int xlen = s.p[0] | (s.p[1] << 8);
+            s.p += 2;
+            if (s.seg_end - s.p < xlen) { err = 1; break; }
+            s.p += xlen;
+        }
+        for (int f = 8; f <= 16 && !err; f <<= 1) {   // FNAME, FCOMMENT: zero-terminated
+            if (!(flg & f)) continue;
+            while (s.p < s.seg_end && *s.p) s.p++;
+            if (s.p >= s.seg_end) err = 1; else s.p++;
+        }
+        if (!err && (flg & 2)) {        // FHCRC
+            if (s.seg_end - s.p < 2) err = 1; else s.p += 2;
+        }
+        if (err) break;
+        Bits b;
+        b.buf = 0;
+        b.cnt = 0;
+        const int64_t before = op;
+        if (deflate_blocks(b, s, dst, dst_n, ws, op)) { err = 3; break; }
+        if (s.seg_end - s.p < 8) { err = 1; break; }      // CRC32 (not verified), ISIZE
+        const uint32_t isize = (uint32_t)s.p[4] | ((uint32_t)s.p[5] << 8) | ((uint32_t)s.p[6] << 16) | ((uint32_t)s.p[7] << 24);
+        if (isize != (uint32_t)(op - before)) { err = 4; break; }
+        s.p += 8;
+    }
+    if (!err && op != dst_n) err = 5;
+    if (err && atomicCAS(status, 0, (int)DE_GZIP_CORRUPT) == 0) { status[1] = pi; status[2] = err; }
+}
+
 }  // namespace
 
 int64_t png_work_bytes(int height, int width, int channels, int sample_bytes) {
@@ -464,6 +539,14 @@ cudaError_t launch_png_batch(const uint8_t *base, const int64_t *offs, const int
                                                                    sample_bytes, dst, work,
                                                                    png_work_bytes(height, width, channels, sample_bytes),
                                                                    status);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gzip_pages(uint8_t *arena, const DevPage *pages, const int32_t *list, int n, int32_t *status,
+                              cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    k_gzip_pages<<<(n + kPngWarpsPerBlock - 1) / kPngWarpsPerBlock, 32 * kPngWarpsPerBlock, 0, s>>>(arena, pages, list, n,
+                                                                                                     status);
     return cudaGetLastError();
 }
 

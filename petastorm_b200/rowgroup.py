@@ -27,7 +27,7 @@ _DEVICE_ERRORS = {
     6: 'NdarrayCodec blobs in one batch do not share the same .npy header', 7: 'corrupt PNG stream',
     8: 'unsupported PNG variant (interlaced / alpha / bit depth / unexpected geometry)',
     9: 'NGram assumes that the data is sorted by the timestamp field which is not the case',
-    10: 'corrupt BYTE_ARRAY page',
+    10: 'corrupt BYTE_ARRAY page', 11: 'corrupt GZIP page',
 }
 
 

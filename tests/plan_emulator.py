@@ -18,6 +18,15 @@ def _snappy(buf, n):
     return pa.Codec('snappy').decompress(bytes(buf), decompressed_size=n).to_pybytes()
 
 
+def _decompress(codec, buf, n):
+    if codec == 2:
+        import zlib
+        out = zlib.decompress(bytes(buf), 31)
+        assert len(out) == n
+        return out
+    return _snappy(buf, n)
+
+
 def _hybrid(buf, pos, end, bw, count):
     """RLE/bit-packed hybrid -> list of `count` ints (parquet Encodings.md)."""
     out = []
@@ -93,12 +102,12 @@ def decode_plan(plan, native):
         (src_off, img_off, comp, uncomp, nvals, first, def_bytes, rep_bytes, col, kind, enc, codec, def_enc, rep_enc,
          v2c, ordinal) = pg
         payload = arena[src_off:src_off + comp]
-        if codec == 1 and comp > 0:
+        if codec in (1, 2) and comp > 0:
             if kind == 3:
                 lv = def_bytes + rep_bytes
-                img = bytes(payload[:lv]) + _snappy(payload[lv:], uncomp - lv)
+                img = bytes(payload[:lv]) + _decompress(codec, payload[lv:], uncomp - lv)
             else:
-                img = _snappy(payload, uncomp)
+                img = _decompress(codec, payload, uncomp)
         else:
             img = bytes(payload)
         assert len(img) == uncomp, (pi, len(img), uncomp)

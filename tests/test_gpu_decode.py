@@ -98,7 +98,7 @@ def _mixed_table(n, seed=1234):
     return t
 
 
-@pytest.mark.parametrize('compression', ['snappy', 'none'])
+@pytest.mark.parametrize('compression', ['snappy', 'none', 'gzip'])
 @pytest.mark.parametrize('version', ['1.0', '2.0'])
 def test_mixed_columns(tmp_path, compression, version):
     t = _mixed_table(150003)

@@ -336,7 +336,8 @@ def test_sanitize_and_collate_tables():
 # native host side: footer, planner, dataset discovery, legacy schema
 # ---------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize('compression,version,dictionary', [('snappy', '1.0', True), ('none', '2.0', True),
-                                                            ('snappy', '2.0', False)])
+                                                            ('snappy', '2.0', False), ('gzip', '1.0', True),
+                                                            ('gzip', '2.0', False)])
 def test_planner_tables_decode_like_pyarrow(tmp_path, compression, version, dictionary):
     """Thrift footer parse + page-header walk + HBM layout: the raw image and device tables of a plan, interpreted by a
     slow numpy emulator, must reproduce pyarrow's values for every column (nulls, dictionaries, booleans, strings)."""
