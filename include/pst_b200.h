@@ -173,6 +173,13 @@ int pst_gather_rows(uint64_t src, uint64_t idx_i64, int64_t n_out, int64_t row_b
 int pst_npy_batch(uint64_t base, uint64_t offs_i64, uint64_t lens_i32, uint64_t row_idx_i64, int64_t n,
                   int64_t data_off, int64_t payload_bytes, uint64_t dst, uint64_t d_status, uint64_t stream);
 
+/* CompressedNdarrayCodec values (np.savez_compressed ZIP archives): the first member of every selected blob is
+ * inflated (DEFLATE) or copied (stored) into dst[i * member_bytes ..); d_status[0] != 0 when a blob is not a ZIP
+ * archive or its member does not have exactly member_bytes bytes.  The .npy images then go through pst_npy_batch.
+ * Replaces np.load(BytesIO(value))['arr'] -- petastorm/codecs.py:196-198. */
+int pst_zip_inflate_batch(uint64_t base, uint64_t offs_i64, uint64_t lens_i32, uint64_t row_idx_i64, int64_t n,
+                          int64_t member_bytes, uint64_t dst, uint64_t d_status, uint64_t stream);
+
 /* first k bytes of every BYTE_ARRAY value -> dst[n, k] (zero padded).  Lets the host read the .npy / PNG headers of a
  * whole row-group with one small D2H when a field's shape is variable (None dimensions in the Unischema). */
 int pst_blob_prefix(uint64_t base, uint64_t offs_i64, uint64_t lens_i32, int64_t n, int k, uint64_t dst,

@@ -435,6 +435,12 @@ int pst_npy_batch(uint64_t base, uint64_t offs, uint64_t lens, uint64_t row_idx,
                           n, data_off, payload_bytes, (uint8_t *)dst, (int32_t *)d_status, (cudaStream_t)stream),
          "npy_batch")
 }
+int pst_zip_inflate_batch(uint64_t base, uint64_t offs, uint64_t lens, uint64_t row_idx, int64_t n, int64_t member_bytes,
+                          uint64_t dst, uint64_t d_status, uint64_t stream) {
+    WRAP(launch_zip_inflate_batch((const uint8_t *)base, (const int64_t *)offs, (const int32_t *)lens,
+                                  (const int64_t *)row_idx, n, member_bytes, (uint8_t *)dst, (int32_t *)d_status,
+                                  (cudaStream_t)stream), "zip_inflate_batch")
+}
 int pst_blob_prefix(uint64_t base, uint64_t offs, uint64_t lens, int64_t n, int k, uint64_t dst, uint64_t stream) {
     WRAP(launch_blob_prefix((const uint8_t *)base, (const int64_t *)offs, (const int32_t *)lens, n, k, (uint8_t *)dst,
                             (cudaStream_t)stream), "blob_prefix")

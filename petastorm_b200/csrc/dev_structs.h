@@ -17,7 +17,8 @@ enum Enc : uint8_t {
 enum DevErr : int32_t {
     DE_OK = 0, DE_SNAPPY_CORRUPT = 1, DE_LEVELS_CORRUPT = 2, DE_UNSUPPORTED_ENCODING = 3, DE_DICT_INDEX_RANGE = 4,
     DE_PAGE_OVERRUN = 5, DE_NPY_HEADER_MISMATCH = 6, DE_PNG_CORRUPT = 7, DE_PNG_UNSUPPORTED = 8,
-    DE_NGRAM_UNSORTED = 9, DE_BYTE_ARRAY_CORRUPT = 10, DE_GZIP_CORRUPT = 11
+    DE_NGRAM_UNSORTED = 9, DE_BYTE_ARRAY_CORRUPT = 10, DE_GZIP_CORRUPT = 11,
+    DE_ZIP_CORRUPT = 12
 };
 
 constexpr int32_t kSnappyFragment = 65536;

@@ -58,6 +58,9 @@ cudaError_t launch_list_uniform(const uint8_t *rep, const uint8_t *def, int64_t 
                                 int64_t *flags, cudaStream_t s);
 
 // ---- kernels_png.cu (DEFLATE users: PNG images, GZIP-compressed pages)
+cudaError_t launch_zip_inflate_batch(const uint8_t *base, const int64_t *offs, const int32_t *lens,
+                                     const int64_t *row_idx, int64_t n, int64_t member_bytes, uint8_t *dst,
+                                     int32_t *status, cudaStream_t s);
 cudaError_t launch_gzip_pages(uint8_t *arena, const DevPage *pages, const int32_t *list, int n, int32_t *status,
                               cudaStream_t s);
 int64_t png_work_bytes(int height, int width, int channels, int sample_bytes);

@@ -523,6 +523,53 @@ k_gzip_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, con
     if (err && atomicCAS(status, 0, (int)DE_GZIP_CORRUPT) == 0) { status[1] = pi; status[2] = err; }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CompressedNdarrayCodec blobs (np.savez_compressed: a ZIP archive whose first member `arr.npy` is deflated,
+// petastorm/codecs.py:181-198): one warp per blob inflates the first member into dst[i * member_bytes ..).  The .npy
+// images are then turned into the batch tensor by k_npy_batch, exactly like NdarrayCodec values.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * kPngWarpsPerBlock)
+k_zip_inflate_batch(const uint8_t *__restrict__ base, const int64_t *__restrict__ offs, const int32_t *__restrict__ lens,
+                    const int64_t *__restrict__ row_idx, int64_t n, int64_t member_bytes, uint8_t *__restrict__ dst,
+                    int32_t *status) {
+    __shared__ WarpState wstate[kPngWarpsPerBlock];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpState &ws = wstate[warp];
+    const int64_t i = (int64_t)blockIdx.x * kPngWarpsPerBlock + warp;
+    if (i >= n || lane != 0) return;
+    const int64_t r = row_idx ? row_idx[i] : i;
+    const uint8_t *blob = base + offs[r];
+    const int64_t blen = lens[r];
+    uint8_t *out = dst + i * member_bytes;
+    int err = 0;
+    auto u16 = [&](int o) { return (int)blob[o] | ((int)blob[o + 1] << 8); };
+    if (blen < 30 || blob[0] != 'P' || blob[1] != 'K' || blob[2] != 3 || blob[3] != 4) err = 1;
+    else if (u16(6) & 1) err = 2;                            // encrypted
+    if (!err) {
+        const int method = u16(8);
+        const int64_t data_off = 30 + (int64_t)u16(26) + u16(28);
+        if (data_off > blen) err = 1;
+        else if (method == 8) {
+            Src s;
+            s.p = blob + data_off;
+            s.seg_end = s.blob_end = blob + blen;
+            s.eof = true;
+            Bits b;
+            b.buf = 0;
+            b.cnt = 0;
+            int64_t op = 0;
+            if (deflate_blocks(b, s, out, member_bytes, ws, op)) err = 3;
+            else if (op != member_bytes) err = 4;
+        } else if (method == 0) {
+            if (data_off + member_bytes > blen) err = 4;
+            else for (int64_t k = 0; k < member_bytes; k++) out[k] = blob[data_off + k];
+        } else {
+            err = 5;
+        }
+    }
+    if (err && atomicCAS(status, 0, (int)DE_ZIP_CORRUPT) == 0) { status[1] = (int)i; status[2] = err; }
+}
+
 }  // namespace
 
 int64_t png_work_bytes(int height, int width, int channels, int sample_bytes) {
@@ -539,6 +586,16 @@ cudaError_t launch_png_batch(const uint8_t *base, const int64_t *offs, const int
                                                                    sample_bytes, dst, work,
                                                                    png_work_bytes(height, width, channels, sample_bytes),
                                                                    status);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_zip_inflate_batch(const uint8_t *base, const int64_t *offs, const int32_t *lens,
+                                     const int64_t *row_idx, int64_t n, int64_t member_bytes, uint8_t *dst,
+                                     int32_t *status, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    int64_t blocks = (n + kPngWarpsPerBlock - 1) / kPngWarpsPerBlock;
+    k_zip_inflate_batch<<<(unsigned)blocks, 32 * kPngWarpsPerBlock, 0, s>>>(base, offs, lens, row_idx, n, member_bytes,
+                                                                           dst, status);
     return cudaGetLastError();
 }
 

@@ -155,6 +155,29 @@ def npy_batch(col, data_off, payload_bytes, torch_dtype, shape, row_index=None):
     return out, status
 
 
+class _DenseBlobs(object):
+    """Fixed-size blobs stored back to back in one device tensor, addressed like a BYTE_ARRAY column."""
+
+    def __init__(self, data, n, blob_bytes):
+        self.arena = data
+        self.num_values = n
+        self.offs = torch.arange(n, dtype=torch.int64, device=data.device) * blob_bytes
+        self.lens = torch.full((n,), blob_bytes, dtype=torch.int32, device=data.device)
+
+
+def zip_inflate_batch(col, member_bytes, row_index=None):
+    """First member of every (selected) ZIP blob of a BYTE_ARRAY column -> _DenseBlobs of .npy images + status."""
+    n = col.num_values if row_index is None else row_index.numel()
+    dev = col.offs.device
+    out = torch.empty((n, member_bytes), dtype=torch.uint8, device=dev)
+    status = _status(dev)
+    if n:
+        check(lib.pst_zip_inflate_batch(col.arena.data_ptr(), col.offs.data_ptr(), col.lens.data_ptr(),
+                                        0 if row_index is None else row_index.data_ptr(), n, member_bytes,
+                                        out.data_ptr(), status.data_ptr(), _stream()), 'zip_inflate_batch')
+    return _DenseBlobs(out, n, member_bytes), status
+
+
 def blob_prefix(col, k):
     """uint8 [n, k] tensor holding the first k bytes of every value of a BYTE_ARRAY column."""
     n = col.num_values

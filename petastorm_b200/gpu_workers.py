@@ -825,8 +825,7 @@ class GpuPyDictWorker(_GpuWorkerBase):
         if order is not None or nulls:
             live_dev = torch.from_numpy(np.ascontiguousarray(live.astype(np.int64))).to(device)
         if isinstance(codec, CompressedNdarrayCodec):
-            blobs = rowgroup.gather_blobs_to_host(col, live)
-            dense = [codec.decode(field, b) for b in blobs]   # zip container parsing stays on the host for now
+            dense = self._decode_zipnpy(col, field, codec, live, live_dev)
         elif isinstance(codec, NdarrayCodec):
             dense = self._decode_npy(col, field, live, live_dev)
         elif codec.image_codec == 'png':
@@ -845,6 +844,33 @@ class GpuPyDictWorker(_GpuWorkerBase):
             else:
                 out.append(None)
         return out
+
+    def _decode_zipnpy(self, col, field, codec, live, live_dev):
+        """CompressedNdarrayCodec: the first blob is opened on the host to learn the .npy header and size of the
+        member; all blobs are then inflated on the device (one warp each) and decoded like NdarrayCodec values.
+        Ragged shapes, string dtypes or anything unexpected fall back to the reference's host decode."""
+        if len(live) == 0:
+            return []
+        import io
+        import zipfile
+        try:
+            first = rowgroup.gather_blobs_to_host(col, live[:1])[0]
+            with zipfile.ZipFile(io.BytesIO(first)) as z:
+                member = z.read(z.infolist()[0])
+            dtype, shape, fortran, data_off = parse_npy_header(member[:min(len(member), 1024)])
+            ok = dtype in _TORCH_OF_NUMPY and not fortran and dtype.byteorder in ('=', '<', '|')
+        except Exception:  # pylint: disable=broad-except
+            ok = False
+        if ok:
+            payload = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+            if data_off + payload == len(member):
+                dense_blobs, st = device_ops.zip_inflate_batch(col, len(member), live_dev)
+                if int(st[0].item()) == 0:
+                    out, status = device_ops.npy_batch(dense_blobs, data_off, payload, _TORCH_OF_NUMPY[dtype], shape)
+                    if int(status[0].item()) == 0:
+                        return out
+        blobs = rowgroup.gather_blobs_to_host(col, live)
+        return [codec.decode(field, b) for b in blobs]
 
     def _decode_npy(self, col, field, live, live_dev):
         if len(live) == 0:

@@ -89,6 +89,7 @@ _sig('pst_narrow_int32', c_int, c_uint64, c_int64, c_int, c_uint64, c_uint64)
 _sig('pst_gather_rows', c_int, c_uint64, c_uint64, c_int64, c_int64, c_uint64, c_uint64)
 _sig('pst_npy_batch', c_int, c_uint64, c_uint64, c_uint64, c_uint64, c_int64, c_int64, c_int64, c_uint64, c_uint64,
      c_uint64)
+_sig('pst_zip_inflate_batch', c_int, c_uint64, c_uint64, c_uint64, c_uint64, c_int64, c_int64, c_uint64, c_uint64, c_uint64)
 _sig('pst_blob_prefix', c_int, c_uint64, c_uint64, c_uint64, c_int64, c_int, c_uint64, c_uint64)
 _sig('pst_png_work_bytes', c_int64, c_int, c_int, c_int, c_int)
 _sig('pst_png_batch', c_int, c_uint64, c_uint64, c_uint64, c_uint64, c_int64, c_int, c_int, c_int, c_int, c_uint64,
@@ -113,7 +114,7 @@ EXPORTED = [
     'pst_file_schema_json', 'pst_file_kv_metadata', 'pst_file_num_kv', 'pst_file_kv_at', 'pst_file_chunk_info',
     'pst_plan_create', 'pst_plan_destroy', 'pst_plan_get_info', 'pst_plan_get_column', 'pst_plan_fill_raw',
     'pst_ctx_create', 'pst_ctx_destroy', 'pst_ctx_stats_json', 'pst_plan_upload', 'pst_plan_decode', 'pst_plan_decode_timed',
-    'pst_nullable_to_f64', 'pst_narrow_int32', 'pst_gather_rows', 'pst_npy_batch', 'pst_blob_prefix', 'pst_png_work_bytes',
+    'pst_nullable_to_f64', 'pst_narrow_int32', 'pst_gather_rows', 'pst_npy_batch', 'pst_blob_prefix', 'pst_zip_inflate_batch', 'pst_png_work_bytes',
     'pst_png_batch', 'pst_jpeg_available', 'pst_jpeg_backend', 'pst_jpeg_batch', 'pst_mask_in_set_i64',
     'pst_mask_md5_split_i64', 'pst_compact_tmp_bytes', 'pst_mask_compact', 'pst_normalize',
     'pst_ngram_valid_starts', 'pst_ngram_gather', 'pst_sanitize', 'pst_list_uniform',
