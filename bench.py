@@ -194,7 +194,7 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rows_pg = args.rows_per_group
-    n_groups = max(args.row_groups, world)
+    n_groups = max(args.row_groups, 2 * world)    # every rank cycles over at least two distinct row-groups
     cores = os.cpu_count() or 1
     cpu_workers = args.cpu_workers or min(cores, 64)
 

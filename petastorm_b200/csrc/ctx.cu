@@ -219,8 +219,9 @@ static int launch_snappy_stage(pst_plan *p, uint8_t *arena, int32_t *status, cud
     const int n_frags = (int)p->snappy_frags.size(), n_multi = (int)p->multi_pages.size();
     int nl = 0;
     if (ev) ck(cudaEventRecord(ev[0], s), "record");
-    if (n_multi > 0) {
-        ck(launch_snappy_index(arena, pages, multi, n_multi, frag_pos, page_flag, s), "snappy index launch");
+    if (!p->index_pages.empty()) {
+        ck(launch_snappy_index(arena, pages, (const int32_t *)(arena + p->index_list_off), (int)p->index_pages.size(),
+                               frag_pos, page_flag, s), "snappy index launch");
         nl++;
     }
     if (ev) ck(cudaEventRecord(ev[1], s), "record");

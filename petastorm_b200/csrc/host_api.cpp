@@ -255,6 +255,50 @@ static int64_t v1_values_offset(const uint8_t *payload, size_t n, int codec, int
     return (int64_t)pos;
 }
 
+// Incompressible data leaves the Snappy compressor as one literal element per 64 KiB block.  Such a stream needs no
+// device-side index: the fragment boundaries are read off the (few) tag bytes right here.  Returns false for anything
+// else; pos[0..nfrag] receives the compressed offsets (same convention as k_snappy_index).
+static bool literal_only_fragments(const uint8_t *s, int64_t n, int64_t ulen, int nfrag, uint32_t *pos) {
+    int64_t ip = 0;
+    uint64_t v = 0;
+    for (int shift = 0;; shift += 7) {
+        if (ip >= n || shift > 35) return false;
+        const uint8_t b = s[ip++];
+        v |= (uint64_t)(b & 0x7f) << shift;
+        if (!(b & 0x80)) break;
+    }
+    if ((int64_t)v != ulen) return false;
+    int64_t op = 0;
+    pos[0] = 0;
+    for (int k = 0; k < nfrag; k++) {
+        if (k > 0) pos[k] = (uint32_t)ip;
+        const int64_t want = std::min<int64_t>(kSnappyFragment, ulen - op);
+        if (ip >= n) return false;
+        const uint8_t tag = s[ip];
+        if ((tag & 3) != 0) return false;
+        const int t6 = tag >> 2;
+        int64_t len, hdr;
+        if (t6 < 60) {
+            len = t6 + 1;
+            hdr = 1;
+        } else {
+            const int nb = t6 - 59;
+            if (ip + 1 + nb > n) return false;
+            len = 0;
+            for (int i = 0; i < nb; i++) len |= (int64_t)s[ip + 1 + i] << (8 * i);
+            len += 1;
+            hdr = 1 + nb;
+        }
+        if (len != want) return false;
+        ip += hdr + len;
+        op += len;
+        if (ip > n) return false;
+    }
+    if (ip != n || op != ulen) return false;
+    pos[nfrag] = (uint32_t)n;
+    return true;
+}
+
 int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_plan **out) {
     PST_TRY
     *out = nullptr;
@@ -391,9 +435,14 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
                     d.nfrag = (int32_t)std::max<int64_t>(1, (values_uncomp + kSnappyFragment - 1) / kSnappyFragment);
                     d.frag_first = (int32_t)p->frag_pos_count;
                     p->frag_pos_count += d.nfrag + 1;
+                    p->frag_pos_host.resize((size_t)p->frag_pos_count, 0u);
                     if (d.nfrag > 1) {
                         d.multi_slot = (int32_t)p->multi_pages.size();
                         p->multi_pages.push_back((int32_t)p->pages.size());
+                        const int64_t lv = (int64_t)d.uncomp_size - values_uncomp;   // V2: uncompressed level bytes
+                        if (!literal_only_fragments(f->map + payload + lv, (int64_t)d.comp_size - lv, values_uncomp, d.nfrag,
+                                                    p->frag_pos_host.data() + d.frag_first))
+                            p->index_pages.push_back((int32_t)p->pages.size());
                     }
                     for (int32_t k = 0; k < d.nfrag; k++)
                         p->snappy_frags.push_back(SnFrag{(int32_t)p->pages.size(), k});
@@ -428,6 +477,7 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
                      [&](const SnFrag &a, const SnFrag &b) { return ratio_less(a.page, b.page); });
     {   // same order for the index kernel; multi_slot follows the sorted list
         std::stable_sort(p->multi_pages.begin(), p->multi_pages.end(), ratio_less);
+        std::stable_sort(p->index_pages.begin(), p->index_pages.end(), ratio_less);
         for (size_t i = 0; i < p->multi_pages.size(); i++) p->pages[p->multi_pages[i]].d.multi_slot = (int32_t)i;
     }
 
@@ -442,15 +492,13 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
     p->frag_list_off = align_up(p->dict_list_off + 4 * (int64_t)p->ba_dict_pages.size(), 16);
     p->multi_list_off = align_up(p->frag_list_off + (int64_t)sizeof(SnFrag) * (int64_t)p->snappy_frags.size(), 16);
     p->gzip_list_off = align_up(p->multi_list_off + 4 * (int64_t)p->multi_pages.size(), 16);
-    p->raw_bytes = align_up(p->gzip_list_off + 4 * (int64_t)p->gzip_pages.size(), 256);
+    p->index_list_off = align_up(p->gzip_list_off + 4 * (int64_t)p->gzip_pages.size(), 16);
+    // fragment positions (host-filled for literal-only pages, written by k_snappy_index for the others) and page flags
+    // (zero; raised on the device): part of the raw image so that every upload resets them
+    p->frag_pos_off = align_up(p->index_list_off + 4 * (int64_t)p->index_pages.size(), 16);
+    p->page_flag_off = align_up(p->frag_pos_off + 4 * p->frag_pos_count, 16);
+    p->raw_bytes = align_up(p->page_flag_off + 4 * (int64_t)p->multi_pages.size(), 256);
     p->scratch_off = p->raw_bytes;
-    {   // device-written tables of the Snappy fragment index (behind the page images)
-        int64_t rel = align_up(scratch_cur, 16);
-        p->frag_pos_off = p->scratch_off + rel;
-        rel = align_up(rel + 4 * p->frag_pos_count, 16);
-        p->page_flag_off = p->scratch_off + rel;
-        scratch_cur = rel + 4 * (int64_t)p->multi_pages.size();
-    }
     p->arena_bytes = align_up(p->scratch_off + scratch_cur + 256, 256);
 
     for (size_t i = 0; i < p->pages.size(); i++)
@@ -507,6 +555,10 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
         memcpy(t + (p->multi_list_off - p->tables_off), p->multi_pages.data(), 4 * p->multi_pages.size());
     if (!p->gzip_pages.empty())
         memcpy(t + (p->gzip_list_off - p->tables_off), p->gzip_pages.data(), 4 * p->gzip_pages.size());
+    if (!p->index_pages.empty())
+        memcpy(t + (p->index_list_off - p->tables_off), p->index_pages.data(), 4 * p->index_pages.size());
+    if (!p->frag_pos_host.empty())
+        memcpy(t + (p->frag_pos_off - p->tables_off), p->frag_pos_host.data(), 4 * p->frag_pos_host.size());
 
     // cache key: file identity + row group + column set
     uint64_t key = 1469598103934665603ull;

@@ -34,6 +34,8 @@ struct pst_plan {
     std::vector<pst::SnFrag> snappy_frags;   // (page, fragment) work items of the Snappy fragment kernel
     std::vector<int32_t> multi_pages;        // compressed pages with more than one fragment (indexed first)
     std::vector<int32_t> gzip_pages;         // page indices compressed with GZIP
+    std::vector<int32_t> index_pages;        // multi-fragment pages whose fragment positions the device has to find
+    std::vector<uint32_t> frag_pos_host;     // fragment-position table as far as the host knows it (literal-only pages)
     int64_t frag_pos_count = 0;              // entries of the fragment-position table (sum of nfrag + 1)
     int64_t num_rows = 0;
     int64_t payload_bytes = 0;
@@ -41,8 +43,8 @@ struct pst_plan {
     // arena layout
     int64_t tables_off = 0;      // offset of the tables inside the raw region
     int64_t cols_off = 0, pages_off = 0, comp_list_off = 0, data_list_off = 0, dict_list_off = 0;
-    int64_t frag_list_off = 0, multi_list_off = 0, gzip_list_off = 0;   // tables (raw region)
-    int64_t frag_pos_off = 0, page_flag_off = 0;     // device-written, scratch region
+    int64_t frag_list_off = 0, multi_list_off = 0, gzip_list_off = 0, index_list_off = 0;   // tables (raw region)
+    int64_t frag_pos_off = 0, page_flag_off = 0;     // raw region too, completed / raised by the device
     int64_t raw_bytes = 0;
     int64_t scratch_off = 0;     // == align(raw_bytes)
     int64_t arena_bytes = 0;
