@@ -233,6 +233,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
+        # stdout carries the JSON line: keep NCCL's version banner (printf to stdout at NCCL_DEBUG=VERSION or WARN) off
+        # it unless somebody asked for a more verbose level on purpose
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION', 'WARN'):
+            os.environ['NCCL_DEBUG'] = 'NONE'
         dist.init_process_group('nccl', device_id=dev)
     if rank == 0:
         url = ensure_dataset(n_groups, rows_pg)
