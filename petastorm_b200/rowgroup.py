@@ -7,6 +7,7 @@ Ownership rule: every decoded row-group owns its HBM (``arena`` = raw page bytes
 decoded columns) through ordinary torch tensors; column tensors handed to users are views that keep ``out`` alive, so
 nothing is recycled under the user (the reference never reuses output buffers either - SURVEY 8b).
 """
+import collections
 import os
 import threading
 from ctypes import byref, c_int
@@ -188,14 +189,27 @@ class RowGroupDecoder(object):
         # overwrite the arena as soon as it is *enqueued* behind the previous decode (numeric-only plans; BYTE_ARRAY
         # columns keep pointing into their arena and get a private one)
         self._stream_arena = {}
+        self._plans = collections.OrderedDict()
         self._next_stream = 0
         self.stream = self.streams[0]
         self.launches = 0
         self.h2d_bytes = 0
         self.host_seconds = [0.0, 0.0, 0.0]  # plan / upload / decode-issue (diagnostics)
 
+    PLAN_CACHE_ENTRIES = 128
+
     def plan(self, path, row_group, leaf_columns):
-        return native.Plan(open_file(path), row_group, leaf_columns)
+        """Plans are immutable (page walk + HBM layout of one row-group / column set): later epochs reuse them."""
+        key = (path, row_group, tuple(leaf_columns))
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = native.Plan(open_file(path), row_group, leaf_columns)
+            self._plans[key] = plan
+            if len(self._plans) > self.PLAN_CACHE_ENTRIES:
+                self._plans.popitem(last=False)
+        else:
+            self._plans.move_to_end(key)
+        return plan
 
     def next_stream(self):
         s = self.streams[self._next_stream]
