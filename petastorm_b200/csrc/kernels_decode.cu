@@ -107,28 +107,31 @@ __device__ __forceinline__ void coop_fill(uint8_t *dst, uint8_t v, int64_t n, in
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K2  Snappy (raw block format, google/snappy format_description.txt).  One CTA = one fragment (or, in the serial
-// fallback launch, one whole page) = two warps:
+// K2  Snappy (raw block format, google/snappy format_description.txt).  One CTA = one 64 KiB fragment (or, in the serial
+// fallback launch, one whole page) = three warps working as a pipeline over batches of <= 32 elements:
 //
-//   warp P (parser)    walks the element stream -- an inherently serial chain, every tag position depends on the
-//                      previous element -- with as few instructions per element as possible: tag bytes come from a
-//                      shared-memory staging window filled by cp.async (LDGSTS), and the only output is one 8-byte
-//                      record {source/offset, length|kind} per element, written to a double-buffered batch in shared
-//                      memory (<= 32 elements, <= 1 KiB of input, <= 4 KiB of output per batch).
-//   warp X (executor)  takes one element per lane: a warp scan of the lengths gives every element its output
-//                      position, literal bytes go staging -> ring, back-references ring -> ring in dependency rounds
-//                      (a copy runs once every element in front of its source range is complete).  The ring holds the
-//                      most recent 16 KiB of output in shared memory, so the many tiny copies of a match-heavy stream
-//                      never pay a global store -> L2 -> global load round trip; it is written through to HBM in
-//                      >= 4 KiB pieces with destination-aligned 16-byte stores.
+//   warp P (parser)     finds where the elements START -- the inherently serial part, every tag position depends on the
+//                       previous element.  Tag bytes come from a shared-memory staging window filled by cp.async
+//                       (LDGSTS); for every 1 KiB of input all 32 lanes build successor tables (element length for
+//                       every byte position, then the lengths of the four elements that follow each position), so
+//                       the chain costs one LDS + one dp4a per FOUR elements.  Output: <= 8 hop records per batch.
+//   warp A (placement)  decodes one element per lane, assigns output positions with a warp scan, validates, and moves
+//                       literal bytes staging -> ring.
+//   warp B (copy)       resolves back-references ring -> ring in dependency rounds (a copy runs once every element in
+//                       front of its source range is complete) and writes the ring through to HBM in >= 4 KiB
+//                       pieces (positions are biased so that ring and HBM agree modulo 16: plain 16-byte copies).
 //
-// The two warps hand batches over with named barriers (bar.arrive / bar.sync), so P parses batch b+1 while X executes
-// batch b.  Literals >= 1 KiB bypass staging and ring (one vectorised global -> global copy by X).  A back-reference
-// that reaches outside the ring, or into a bypassed literal, is served from the output already written to HBM.
+// The ring holds the most recent 16 KiB of output in shared memory, so the many tiny copies of a match-heavy stream
+// never pay a global store -> L2 -> global load round trip.  Neighbouring warps hand batches over by a rendezvous on
+// one named barrier per pair (double-buffered slots): P parses batch b+1 while A places batch b and B copies batch
+// b-1.  Literals >= 1 KiB bypass staging and ring (one vectorised global -> global copy by B).  A back-reference that
+// reaches outside the ring, or into a bypassed literal, is served from the output already written to HBM.
 //
-// Why this shape: measured on B200 (profiles/r1_snappy_v2_ring.txt) a lone warp retires ~1 dependent instruction per
-// ~5 cycles, so the cost of a page is (instructions on the serial chain) x 5 cycles x elements; the 1 MiB dictionary
-// page of a C2 int64 column has 2.3e5 elements and sets the latency of the whole row-group.
+// Why this shape: measured on B200 (profiles/r1_snappy_v2_ring.txt ... r1_final_three_stage.txt) a lone warp retires
+// ~1 dependent instruction per ~5.5 cycles and a taken branch costs ~15, so the cost of a stream is (instructions on
+// the serial chain) x 5.5 cycles x elements; a 1 MiB page of a C2 int64 column has 2.3e5 elements.  Hence: shortest
+// possible serial chain (tables), the rest of the per-element work spread over 32 lanes and three warps, and 64 KiB
+// fragments (k_snappy_index) so that a page is 16 CTAs instead of one.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane);   // defined with the page decoder below
 
