@@ -12,6 +12,7 @@ Arguments that only make sense for the CPU pools (``workers_count``, ``results_q
 """
 import collections.abc
 import logging
+import os
 import random
 import warnings
 
@@ -47,9 +48,11 @@ def _make_cache(cache_type, cache_location, cache_size_limit, cache_row_size_est
 
 def _make_pool(reader_pool_type, workers_count, results_queue_size, device):
     if reader_pool_type in ('thread', 'process'):
-        # `workers_count` here only sizes the ventilation window (2 * 4 = 8 row-groups in flight): deep enough to keep
-        # the PCIe copy engine busy while ~4 earlier row-groups are still in their (latency-bound) decode kernels
-        return GpuPool(workers_count=2, results_queue_size=min(max(int(results_queue_size), 1), 6), device=device)
+        # row-groups in flight: one being consumed, one or two decoding (~3 ms), one copying (~5 ms), one queued behind
+        # it so that the PCIe copy engine never idles
+        pool = GpuPool(workers_count=1, results_queue_size=min(max(int(results_queue_size), 1), 6), device=device)
+        pool.max_in_flight = int(os.environ.get('PST_MAX_IN_FLIGHT', '6'))
+        return pool
     if reader_pool_type == 'dummy':
         return GpuPool(synchronous=True, device=device)
     raise ValueError('Unknown reader_pool_type: {}'.format(reader_pool_type))
@@ -225,6 +228,7 @@ class Reader(object):
         normalized_drop = self._normalize_shuffle_options(shuffle_row_drop_partitions, row_groups)
         self.ventilator = self._create_ventilator(filtered_row_group_indexes, shuffle_row_groups, normalized_drop,
                                                   self.num_epochs, worker_predicate,
+                                                  getattr(self._workers_pool, 'max_in_flight', None) or
                                                   self._workers_pool.workers_count * (1 + _VENTILATE_EXTRA_ROWGROUPS),
                                                   seed)
 
