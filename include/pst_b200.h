@@ -97,7 +97,8 @@ typedef struct pst_plan_info {
     int32_t num_pages;
     int32_t num_columns;
     int32_t num_compressed_pages;
-    int32_t reserved;
+    int32_t num_index_pages; /* Snappy pages whose 64 KiB fragment boundaries the device has to find (k_snappy_index);
+                                pages made of one literal per block are resolved by the planner */
 } pst_plan_info;
 int pst_plan_get_info(const pst_plan *p, pst_plan_info *out);
 

@@ -592,7 +592,7 @@ int pst_plan_get_info(const pst_plan *p, pst_plan_info *out) {
     out->num_pages = (int32_t)p->pages.size();
     out->num_columns = (int32_t)p->cols.size();
     out->num_compressed_pages = (int32_t)(p->compressed_pages.size() + p->gzip_pages.size());
-    out->reserved = 0;
+    out->num_index_pages = (int32_t)p->index_pages.size();
     return 0;
 }
 

@@ -42,7 +42,7 @@ class ChunkInfo(Structure):
 class PlanInfo(Structure):
     _fields_ = [('num_rows', c_int64), ('raw_bytes', c_int64), ('arena_bytes', c_int64), ('out_bytes', c_int64),
                 ('payload_bytes', c_int64), ('uncompressed_bytes', c_int64), ('num_pages', c_int32),
-                ('num_columns', c_int32), ('num_compressed_pages', c_int32), ('reserved', c_int32)]
+                ('num_columns', c_int32), ('num_compressed_pages', c_int32), ('num_index_pages', c_int32)]
 
 
 class PlanColumn(Structure):

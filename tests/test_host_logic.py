@@ -529,3 +529,22 @@ def test_partition_filters_follow_legacy_pyarrow_semantics(tmp_path):
         dm.ParquetDataset(path, filters=[('part', '~', 1)])
     with pytest.raises(TypeError):
         dm.ParquetDataset(path, filters=[('part', 'in', 1)])
+
+
+def test_planner_resolves_literal_only_snappy_pages_on_the_host(tmp_path):
+    """Incompressible pages leave snappy::RawCompress as one literal per 64 KiB block: the planner reads the fragment
+    boundaries off the tag bytes, and only compressible multi-fragment pages are left for k_snappy_index."""
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    from petastorm_b200 import native
+    n = 300000
+    rng = np.random.default_rng(0)
+    path = str(tmp_path / 'x.parquet')
+    pq.write_table(pa.table({'noise': rng.integers(0, 2 ** 63 - 1, n, dtype=np.int64),
+                             'narrow': rng.integers(0, 2 ** 20, n, dtype=np.int64)}),
+                   path, compression='snappy', use_dictionary=False, data_page_size=1 << 20)
+    f = native.ParquetFile(path)
+    noise = native.Plan(f, 0, [0]).info
+    narrow = native.Plan(f, 0, [1]).info
+    assert noise.num_compressed_pages >= 2 and noise.num_index_pages == 0
+    assert narrow.num_compressed_pages >= 2 and narrow.num_index_pages == narrow.num_compressed_pages
