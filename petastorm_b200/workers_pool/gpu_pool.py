@@ -19,6 +19,22 @@ from petastorm_b200.workers_pool import EmptyResultError, VentilatedItemProcesse
 _POLL = 0.005
 
 
+class WorkerBase(object):
+    """What a pool expects of a worker class (the reference's plug-in seam #1): it is constructed as
+    ``worker_class(worker_id, publish_func, args)``, receives every ventilated item through ``process(**item)`` -
+    publishing zero or more results with ``self.publish_func(result)`` - and is told to release its resources with
+    ``shutdown()`` when the pool is joined."""
+
+    def __init__(self, worker_id, publish_func, args):
+        self.worker_id, self.publish_func, self.args = worker_id, publish_func, args
+
+    def process(self, *args, **kargs):
+        raise NotImplementedError('{} does not implement process()'.format(type(self).__name__))
+
+    def shutdown(self):
+        """Nothing to release by default."""
+
+
 class WorkerTerminationRequested(Exception):
     """Raised inside a worker thread when the pool is being stopped."""
 

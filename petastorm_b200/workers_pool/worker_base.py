@@ -1,14 +1,2 @@
-"""Worker protocol (petastorm/workers_pool/worker_base.py:18-35)."""
-
-
-class WorkerBase(object):
-    def __init__(self, worker_id, publish_func, args):
-        self.worker_id = worker_id
-        self.publish_func = publish_func
-        self.args = args
-
-    def process(self, *args, **kargs):
-        raise NotImplementedError
-
-    def shutdown(self):
-        pass
+"""Import location kept for code written against ``petastorm.workers_pool.worker_base``."""
+from petastorm_b200.workers_pool.gpu_pool import WorkerBase  # noqa: F401
