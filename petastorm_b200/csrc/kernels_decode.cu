@@ -1280,9 +1280,10 @@ k_decode_pages(uint8_t *__restrict__ arena, uint8_t *__restrict__ out, const Dev
         if (!all_valid) {
             if (!hybrid_fill(sh.def_c, sh.table, sh.s_def, tn)) { if (tid == 0) report_error(status, DE_LEVELS_CORRUPT, pi, 11); return; }
         }
-        // ranks: exclusive scan of validity, tile laid out item-major (i = k*256 + tid)
-        uint32_t carry = 0;
-        for (uint32_t k = 0; k < tn; k += kDecThreads) {
+        // ranks: exclusive scan of validity, tile laid out item-major (i = k*256 + tid); without nulls the rank of an
+        // entry is its position and the scan (two block barriers per 256 entries) is skipped
+        uint32_t carry = all_valid ? tn : 0;
+        for (uint32_t k = 0; !all_valid && k < tn; k += kDecThreads) {
             uint32_t i = k + tid;
             uint32_t v = (i < tn) ? (all_valid ? 1u : (sh.s_def[i] == (uint32_t)col.max_def ? 1u : 0u)) : 0u;
             uint32_t incl = warp_incl_scan(v, lane);
@@ -1330,7 +1331,7 @@ k_decode_pages(uint8_t *__restrict__ arena, uint8_t *__restrict__ out, const Dev
         for (uint32_t i = tid; i < tn; i += kDecThreads) {
             const int64_t row = first + base + i;
             const bool valid = all_valid || sh.s_def[i] == (uint32_t)col.max_def;
-            const uint32_t r = sh.s_rank[i];            // tile-relative rank
+            const uint32_t r = all_valid ? i : sh.s_rank[i];   // tile-relative rank
             const uint64_t gr = (uint64_t)rank_base + r;  // page-relative rank
             if (o_valid) o_valid[row] = valid ? 1 : 0;
             if (o_rep) { o_rep[row] = (uint8_t)sh.s_rep[i]; o_def[row] = (uint8_t)(all_valid ? col.max_def : sh.s_def[i]); }
