@@ -42,7 +42,7 @@ DATA_DIR = os.environ.get('PST_BENCH_DIR', '/tmp/pst_bench_c2')
 # ---------------------------------------------------------------------------------------------------------------------
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the C2 row-group, from the committed ncu --set full capture
 NCU_DRAM_SOURCE = 'profiles/r1_final_three_stage.txt (ncu --set full, one launch on a C2 row-group)'
-NCU_DRAM_BYTES_PER_LAUNCH = {'k_snappy_index': 93603840, 'k_snappy_pages': 553425152, 'k_decode_pages': 570102272}
+NCU_DRAM_BYTES_PER_LAUNCH = {'k_snappy_index': 78018560, 'k_snappy_pages': 554502656, 'k_decode_pages': 569783040}
 
 
 def _write_one(args):
