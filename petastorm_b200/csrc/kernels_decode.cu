@@ -253,7 +253,8 @@ struct SnExec {                 // warp A -> warp B: the back-references of one 
     uint32_t big_src;           // ... and its input offset
     uint32_t last;
     uint32_t failed;
-    uint32_t pad_[3];
+    uint32_t dst_begin;         // output position in front of the batch
+    uint32_t pad_[2];
 };
 static_assert(sizeof(SnExec) == 416, "SnExec layout");
 constexpr uint32_t kExecHdr = kBatchOps * 12;
@@ -627,7 +628,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
             sts_u32(ex_s + 256u + 4u * lane, (is_copy && !failed) ? len : 0u);
             if (lane == 0) {
                 sts_v4(ex_s + kExecHdr, dst0 + total, has_big && !failed ? big_len : 0u, rare.x, last);
-                sts_u32(ex_s + kExecHdr + 16, failed ? 1u : 0u);
+                sts_v2(ex_s + kExecHdr + 16, failed ? 1u : 0u, dst0);
             }
             if (!failed) dst0 += total + (has_big ? big_len : 0u);
             __syncwarp();
@@ -661,7 +662,9 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
             const uint32_t ex_s = execs_s + (uint32_t)s * (uint32_t)sizeof(SnExec);
             const uint4 hdr = lds_v4(ex_s + kExecHdr);
             const uint32_t dst_end = hdr.x, big_len = hdr.y, big_src = hdr.z, last = hdr.w;
-            const bool failed = lds_u32(ex_s + kExecHdr + 16) != 0;
+            const uint2 hdr2 = lds_v2(ex_s + kExecHdr + 16);
+            const bool failed = hdr2.x != 0;
+            const uint32_t dst_begin = hdr2.y;
             if (!failed) {
                 const uint32_t d = lds_u32(ex_s + 4u * lane), a = lds_u32(ex_s + 128u + 4u * lane);
                 const uint32_t len = lds_u32(ex_s + 256u + 4u * lane);
@@ -671,7 +674,14 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                 // warp A may already be placing the literals of the next batch: the oldest kMaxBatchOut bytes of the
                 // ring are not trusted
                 const bool in_ring = sp >= valid_from && dst_end - sp <= (uint32_t)kRing - kMaxBatchOut;
-                uint32_t pending = __ballot_sync(0xffffffffu, is_copy);
+                // the common case first: a source that ends in front of the batch depends on nothing in it
+                const bool early = is_copy && in_ring && src_end <= dst_begin;
+                if (early) {
+                    for (uint32_t i = 0; i < len; i++)
+                        sts_u8(ring_s + ((d + i) & kRingMask), lds_u8(ring_s + ((d + i - a) & kRingMask)));
+                }
+                uint32_t pending = __ballot_sync(0xffffffffu, is_copy && !early);
+                __syncwarp();
                 while (pending) {
                     const int first = __ffs(pending) - 1;
                     const uint32_t done_pos = __shfl_sync(0xffffffffu, d, first);   // everything below is complete
