@@ -283,6 +283,20 @@ def infer_or_load_unischema(dataset):
     return Unischema.from_parquet_schema(first.schema, partition_fields)
 
 
+def update_common_metadata(dataset, key_values):
+    """Adds / replaces key-value pairs of the dataset's ``_common_metadata`` (what ``utils.add_to_dataset_metadata``
+    does for the reference, petastorm/utils.py:95-130).  ``key_values``: bytes -> bytes."""
+    import pyarrow.parquet as pq
+    if dataset.common_metadata_path is None:
+        raise PetastormMetadataError('The dataset has no _common_metadata file to update')
+    arrow_schema = pq.read_schema(dataset.common_metadata_path)
+    meta = dict(arrow_schema.metadata or {})
+    meta.update(key_values)
+    pq.write_metadata(arrow_schema.with_metadata(meta), dataset.common_metadata_path)
+    rowgroup.forget_file(dataset.common_metadata_path)
+    dataset._common_kv = None  # pylint: disable=protected-access
+
+
 def get_row_group_indexes(dataset):
     """Pickled value -> row-group indexes built by ``build_rowgroup_index`` (petastorm/etl/rowgroup_indexing.py:136-158)."""
     common = dataset.common_metadata

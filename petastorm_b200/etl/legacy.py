@@ -40,6 +40,8 @@ class RestrictedUnpickler(pickle.Unpickler):
         if module == 'pyspark.serializers' and name == '_restore':
             return _restore_namedtuple
         for pkg in _LEGACY_PACKAGES:
+            if module == pkg + '.etl.rowgroup_indexers':      # row-group indexes (dataset-toolkit.rowgroups_index.v1)
+                return getattr(importlib.import_module('petastorm_b200.etl.rowgroup_indexers'), name)
             if module.startswith(pkg + '.'):
                 sub = module[len(pkg) + 1:].split('.')[0]
                 if sub in _OWN_MODULES:
@@ -66,6 +68,9 @@ class RestrictedUnpickler(pickle.Unpickler):
             if name in _SAFE_BUILTINS:
                 return getattr(builtins, name)
             raise pickle.UnpicklingError("global '%s.%s' is forbidden" % (module, name))
+        if module == '_codecs' and name == 'encode':
+            import _codecs          # protocol-2 pickles of numpy scalars / bytes written by python 3 go through it
+            return _codecs.encode
         if module in ('copy_reg', 'copyreg'):
             if name in ('_reconstructor', '__newobj__', '__newobj_ex__'):
                 return getattr(copyreg, name)

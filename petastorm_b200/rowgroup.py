@@ -73,6 +73,14 @@ def open_file(path):
         return f
 
 
+def forget_file(path):
+    """Drops one file from the open-file cache (it was rewritten)."""
+    with _ctx_lock:
+        f = _files.pop(path, None)
+        if f is not None:
+            f.close()
+
+
 def forget_files():
     with _ctx_lock:
         for f in _files.values():

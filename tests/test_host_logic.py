@@ -548,3 +548,60 @@ def test_planner_resolves_literal_only_snappy_pages_on_the_host(tmp_path):
     narrow = native.Plan(f, 0, [1]).info
     assert noise.num_compressed_pages >= 2 and noise.num_index_pages == 0
     assert narrow.num_compressed_pages >= 2 and narrow.num_index_pages == narrow.num_compressed_pages
+
+
+def _index_fixture_pieces():
+    pieces = []
+    for p in range(6):
+        rows = []
+        for i in range(5):
+            k = p * 5 + i
+            rows.append({'id': np.int64(k), 'tag': 'tag_%d' % (k % 4), 'sensor': None if p % 2 else 's%d' % (k % 3),
+                         'vec': np.array([k % 3, 7 + p], dtype=np.int32)})
+        pieces.append(rows)
+    return pieces
+
+
+def test_rowgroup_indexers_match_the_reference_classes():
+    """tests/golden/rowgroup_index.json was pickled by the reference's own SingleFieldIndexer / FieldNotNullIndexer
+    (oracle/make_golden_index.py): it must un-pickle onto this package's classes, answer the same look-ups, and this
+    package's indexers must build the same index from the same rows and pickle it under the reference's module name."""
+    import json
+    import pickletools
+    from petastorm_b200.etl.legacy import restricted_loads
+    from petastorm_b200.etl.rowgroup_indexers import (FieldNotNullIndexer, SingleFieldIndexer,
+                                                      pickle_indexers_reference_compatible)
+    from petastorm_b200.selectors import IntersectIndexSelector, SingleIndexSelector, UnionIndexSelector
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'rowgroup_index.json')))
+    ref = restricted_loads(bytes.fromhex(fx['pickle_hex']))
+    mine = {ix.index_name: ix for ix in [SingleFieldIndexer('by_tag', 'tag'), SingleFieldIndexer('by_id', 'id'),
+                                         SingleFieldIndexer('by_vec', 'vec'), FieldNotNullIndexer('has_sensor', 'sensor')]}
+    for piece_index, rows in enumerate(_index_fixture_pieces()):
+        for ix in mine.values():
+            ix.build_index(rows, piece_index)
+    for index_dict in (ref, mine, restricted_loads(pickle_indexers_reference_compatible(mine))):
+        assert isinstance(index_dict['by_tag'], SingleFieldIndexer)
+        assert isinstance(index_dict['has_sensor'], FieldNotNullIndexer)
+        lk = fx['lookups']
+        for v, exp in lk['by_tag'].items():
+            assert sorted(index_dict['by_tag'].get_row_group_indexes(v)) == exp
+        for v, exp in lk['by_id'].items():
+            assert sorted(index_dict['by_id'].get_row_group_indexes(int(v))) == exp
+        for v, exp in lk['by_vec'].items():
+            assert sorted(index_dict['by_vec'].get_row_group_indexes(int(v))) == exp
+        assert sorted(index_dict['has_sensor'].get_row_group_indexes()) == lk['has_sensor']
+        for name, exp in lk['indexed_values'].items():
+            assert sorted(map(str, index_dict[name].indexed_values)) == exp
+        assert index_dict['by_tag'].column_names == ['tag'] and index_dict['by_tag'].index_name == 'by_tag'
+        # selectors: pure set algebra over the index
+        assert SingleIndexSelector('by_tag', ['tag_0']).select_row_groups(index_dict) == set(lk['by_tag']['tag_0'])
+        both = IntersectIndexSelector([SingleIndexSelector('by_id', [7]), SingleIndexSelector('by_tag', ['tag_3'])])
+        assert both.select_row_groups(index_dict) == set(lk['by_id']['7']) & set(lk['by_tag']['tag_3'])
+        either = UnionIndexSelector([SingleIndexSelector('by_id', [0]), SingleIndexSelector('by_id', [29])])
+        assert either.select_row_groups(index_dict) == set(lk['by_id']['0']) | set(lk['by_id']['29'])
+    # the pickle names the reference's module, never this package
+    ops = [str(arg) for op, arg, _ in pickletools.genops(pickle_indexers_reference_compatible(mine)) if op.name == 'GLOBAL']
+    assert any(o.startswith('petastorm.etl.rowgroup_indexers ') for o in ops)
+    assert not any('petastorm_b200' in o for o in ops)
+    with pytest.raises(TypeError):
+        mine['by_tag'] + mine['has_sensor']
