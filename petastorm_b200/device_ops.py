@@ -8,7 +8,6 @@ import math
 import numpy as np
 import torch
 
-from petastorm_b200 import native
 from petastorm_b200.native import lib, check
 
 _NORM_DTYPE = {torch.uint8: 0, torch.float16: 1, torch.float32: 2, torch.int32: 3, torch.int16: 4, torch.uint16: 5,

@@ -12,7 +12,6 @@ kernels, predicates become device masks + stream compaction, and results stay in
 row-group's output buffer).  Values that cannot be tensors (strings, Decimals, dates) are materialised on the host
 after the device did the decompression / level / dictionary work - the reference DataLoader refuses them anyway.
 """
-import datetime
 import hashlib
 from decimal import Decimal
 
@@ -24,7 +23,7 @@ from petastorm_b200.cache import NullCache
 from petastorm_b200.codecs import (CompressedImageCodec, CompressedNdarrayCodec, NdarrayCodec, ScalarCodec,
                                    parse_npy_header)
 from petastorm_b200.errors import DecodeFieldError
-from petastorm_b200.rowgroup import BOOLEAN, BYTE_ARRAY, DOUBLE, FIXED_LEN_BYTE_ARRAY, FLOAT, INT32, INT64, INT96
+from petastorm_b200.rowgroup import BOOLEAN, BYTE_ARRAY, FIXED_LEN_BYTE_ARRAY, INT32, INT64, INT96
 from petastorm_b200.unischema import integer_logical_type
 from petastorm_b200.workers_pool import EmptyResultError
 from petastorm_b200.workers_pool.worker_base import WorkerBase
@@ -956,7 +955,6 @@ class GpuPyDictWorker(_GpuWorkerBase):
         if shape and None not in shape and len(shape) == 3 and shape[2] == 3:
             return device_ops.jpeg_batch(blobs, shape[0], shape[1], col.arena.device)
         # variable geometry: group by the SOF dimensions
-        import struct
         dims = []
         for b in blobs:
             dims.append(_jpeg_size(b))

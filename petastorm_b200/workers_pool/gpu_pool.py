@@ -12,7 +12,6 @@ ventilation order (single issuing thread), which makes seeded runs reproducible.
 import queue
 import sys
 import threading
-from time import sleep
 
 from petastorm_b200.workers_pool import EmptyResultError, VentilatedItemProcessedMessage
 

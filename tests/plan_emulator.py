@@ -4,7 +4,6 @@ It follows the same tables the CUDA kernels read (``petastorm_b200/csrc/dev_stru
 (thrift footer, page walk, HBM layout) can be checked against pyarrow on a machine without a GPU.  It is NOT used by
 the product and is not an oracle for the kernels themselves (the GPU parity tests compare kernel output with pyarrow).
 """
-import ctypes
 import struct
 
 import numpy as np

@@ -1,8 +1,6 @@
 """GPU parity of the page-decode kernels (Snappy, RLE/bit-packed hybrid, PLAIN, dictionary, validity) against Arrow C++
 (pyarrow), the decoder the reference reaches through ``piece.read`` (petastorm/arrow_reader_worker.py:358).
 Bit-exact comparison; everything goes through the C-ABI (petastorm_b200.native)."""
-import os
-
 import numpy as np
 import pyarrow as pa
 import pyarrow.parquet as pq
