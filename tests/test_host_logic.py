@@ -605,3 +605,29 @@ def test_rowgroup_indexers_match_the_reference_classes():
     assert not any('petastorm_b200' in o for o in ops)
     with pytest.raises(TypeError):
         mine['by_tag'] + mine['has_sensor']
+
+
+def test_update_common_metadata_keeps_the_other_keys(tmp_path):
+    """Role of utils.add_to_dataset_metadata (petastorm/utils.py:88-130): adding the row-group index must not lose the
+    unischema / row-groups-per-file entries, and the cached footer of the rewritten file must not be served again."""
+    from petastorm_b200.etl import dataset_metadata as dm
+    from petastorm_b200.etl.rowgroup_indexers import SingleFieldIndexer, pickle_indexers_reference_compatible
+    url = datasets.build('test', str(tmp_path / 't'), 12, row_group_rows=5)
+    path = url[len('file://'):]
+    ds = dm.ParquetDataset(path)
+    before = dict(ds.common_metadata)
+    with pytest.raises(dm.PetastormMetadataError):
+        dm.get_row_group_indexes(ds)
+    ix = SingleFieldIndexer('by_id', 'id')
+    ix.build_index([{'id': np.int32(3)}, {'id': np.int32(4)}], 0)
+    ix.build_index([{'id': np.int32(4)}], 1)
+    dm.update_common_metadata(ds, {dm.ROWGROUPS_INDEX_KEY: pickle_indexers_reference_compatible({'by_id': ix})})
+    for fresh in (ds, dm.ParquetDataset(path)):
+        after = fresh.common_metadata
+        for k, v in before.items():
+            if k != b'ARROW:schema':         # pyarrow's own copy of the schema embeds the key-value metadata
+                assert after[k] == v
+        loaded = dm.get_row_group_indexes(fresh)
+        assert sorted(loaded['by_id'].get_row_group_indexes(4)) == [0, 1]
+        assert sorted(loaded['by_id'].get_row_group_indexes(3)) == [0]
+    assert list(dm.get_schema(dm.ParquetDataset(path)).fields) == list(dm.get_schema(ds).fields)
