@@ -113,20 +113,20 @@ int pst_file_open(const char *path, pst_file **out) {
         throw std::runtime_error(std::string(path) + " is too small to be a parquet file");
     }
     void *map = mmap(nullptr, size, PROT_READ, MAP_SHARED, fd, 0);
-    if (map == MAP_FAILED) {
-        ::close(fd);
-        throw std::runtime_error(std::string("mmap failed for ") + path + ": " + strerror(errno));
-    }
+    const int mmap_errno = errno;
+    ::close(fd);   // the mapping outlives the descriptor: an open file costs no fd (datasets have 10^4..10^5 files)
+    fd = -1;
+    if (map == MAP_FAILED)
+        throw std::runtime_error(std::string("mmap failed for ") + path + ": " + strerror(mmap_errno));
     std::unique_ptr<pst_file> f(new pst_file());
     f->path = path;
-    f->fd = fd;
+    f->fd = -1;
     f->map = static_cast<const uint8_t *>(map);
     f->size = size;
     f->mtime_ns = (int64_t)st.st_mtim.tv_sec * 1000000000ll + st.st_mtim.tv_nsec;
     auto fail = [&](const std::string &m) {
         munmap(map, size);
-        ::close(fd);
-        f->fd = -1;
+        f->map = nullptr;
         throw std::runtime_error(std::string(path) + ": " + m);
     };
     if (memcmp(f->map + size - 4, "PAR1", 4) != 0 || memcmp(f->map, "PAR1", 4) != 0) {

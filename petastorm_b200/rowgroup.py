@@ -38,7 +38,7 @@ class DeviceDecodeError(RuntimeError):
 
 _ctx_lock = threading.Lock()
 _contexts = {}
-_files = {}
+_files = collections.OrderedDict()
 
 #: default budget of the pinned row-group cache (host RAM kept page-locked so that re-reading a row-group in a later
 #: epoch is one cudaMemcpyAsync); override with set_pinned_cache_bytes() before the first reader is created
@@ -63,13 +63,21 @@ def get_context(device=None):
         return ctx
 
 
+OPEN_FILE_CACHE_ENTRIES = 1024
+
+
 def open_file(path):
-    """Cached :class:`native.ParquetFile` (mmap + parsed footer) - host only."""
+    """Cached :class:`native.ParquetFile` (mmap + parsed footer) - host only.  The cache is an LRU: an evicted file is
+    unmapped once the last plan that refers to it is gone (plans keep their file alive)."""
     with _ctx_lock:
         f = _files.get(path)
         if f is None:
             f = native.ParquetFile(path)
             _files[path] = f
+            if len(_files) > OPEN_FILE_CACHE_ENTRIES:
+                _files.popitem(last=False)
+        else:
+            _files.move_to_end(path)
         return f
 
 

@@ -53,6 +53,7 @@ class GpuPool(object):
         self._stop_event = threading.Event()
         self._ventilated_items = 0
         self._ventilated_items_processed = 0
+        self._count_lock = threading.Lock()   # get_results() may be called from several consumer threads
         self._started = False
         self._sync_results = []
 
@@ -94,7 +95,8 @@ class GpuPool(object):
             except queue.Empty:
                 continue
             if isinstance(result, VentilatedItemProcessedMessage):
-                self._ventilated_items_processed += 1
+                with self._count_lock:
+                    self._ventilated_items_processed += 1
                 if self._ventilator:
                     self._ventilator.processed_item()
                 continue
