@@ -41,8 +41,35 @@ DATA_DIR = os.environ.get('PST_BENCH_DIR', '/tmp/pst_bench_c2')
 # synthetic data (np.random.default_rng(1234); float32 ~ N(0,1), int64 ~ U[0, 2^40))
 # ---------------------------------------------------------------------------------------------------------------------
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the C2 row-group, from the committed ncu --set full capture
-NCU_DRAM_SOURCE = 'profiles/r1_final_three_stage.txt (ncu --set full, one launch on a C2 row-group)'
-NCU_DRAM_BYTES_PER_LAUNCH = {'k_snappy_index': 78018560, 'k_snappy_pages': 554502656, 'k_decode_pages': 569783040}
+NCU_DRAM_SOURCE = None   # filled in from the committed ncu --set full capture of this round (profiles/r2_*.txt)
+NCU_DRAM_BYTES_PER_LAUNCH = {}
+
+
+def plan_algorithmic_bytes(plan):
+    """Bytes each decode kernel has to move for one launch on this plan (one row-group), from the planner's page table:
+    index reads the stored bytes of the multi-fragment Snappy pages; fragments read stored + write image bytes of every
+    Snappy page; the tile copy reads and writes the value bytes of PLAIN pages without nulls; the page decoder reads
+    the images of the remaining data pages (+ their dictionaries) and writes their values."""
+    info = plan.info
+    res = dict.fromkeys(['k_snappy_index', 'k_snappy_pages', 'k_snappy_pages(serial fallback)', 'k_ba_dict_index',
+                         'k_copy_tiles', 'k_decode_pages'], 0)
+    dict_bytes = {}
+    for i in range(info.num_pages):
+        pg = plan.page(i)
+        if pg.fragments > 1:
+            res['k_snappy_index'] += pg.stored_bytes
+        if pg.fragments >= 1:
+            res['k_snappy_pages'] += pg.stored_bytes + pg.image_bytes
+        if pg.kind == 2:
+            dict_bytes[pg.column_slot] = pg.image_bytes
+        elif not pg.flags & 2:
+            width = max(plan.cols[pg.column_slot].type_length, 1)
+            res['k_decode_pages'] += pg.image_bytes + pg.num_values * width
+    res['k_decode_pages'] += sum(dict_bytes.values())
+    for i in range(info.num_copy_tiles):
+        t = plan.copy_tile(i)
+        res['k_copy_tiles'] += 2 * t.nbytes + t.nvalid
+    return res
 
 
 def _write_one(args):
@@ -315,36 +342,43 @@ def main():
     # ---- (2) roofline of the dominant kernel, per-kernel CUDA events on the launching stream ---------------------
     from ctypes import c_float
     from petastorm_b200 import native
-    ms_acc = np.zeros(5)
+    ms_acc = np.zeros(6)
     reps = max(4, min(args.steps, 8))
     for k in range(reps):
         j = k % len(plans)
         out = torch.empty(plans[j].info.out_bytes, dtype=torch.uint8, device=dev)
         status = torch.zeros(8 + len(leaves), dtype=torch.int32, device=dev)
-        ms3 = (c_float * 5)()
+        ms6 = (c_float * 6)()
         native.check(native.lib.pst_plan_decode_timed(dec.ctx.handle, plans[j].handle, arenas[j].data_ptr(),
-                                                      out.data_ptr(), status.data_ptr(), stream.cuda_stream, ms3))
-        ms_acc += np.array(list(ms3))
+                                                      out.data_ptr(), status.data_ptr(), stream.cuda_stream, ms6))
+        ms_acc += np.array(list(ms6))
     ms_avg = ms_acc / reps
-    names = ['k_snappy_index', 'k_snappy_pages', 'k_snappy_pages(serial fallback)', 'k_ba_dict_index', 'k_decode_pages']
+    names = ['k_snappy_index', 'k_snappy_pages', 'k_snappy_pages(serial fallback)', 'k_ba_dict_index', 'k_copy_tiles',
+             'k_decode_pages']
     dom = int(np.argmax(ms_avg))
     peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(peaks_path):
         peak, peak_src = json.load(open(peaks_path))['hbm_gbs'], 'measured (MEASURED_PEAKS.json hbm_gbs)'
     else:
         peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
-    # algorithmic bytes per launch (one launch = one row-group): E = stored page bytes, U = uncompressed page images,
-    # D = decoded columns.  index: reads E; fragments: E -> U; page decode: U -> D.
-    U = plans[0].info.uncompressed_bytes
-    algo_by_kernel = [payload, payload + U, payload + U, 0, U + rows_pg * ROW_BYTES]
+    # algorithmic bytes per launch (one launch = one row-group), from the plan's own page table
+    algo = plan_algorithmic_bytes(plans[0])
+    algo_by_kernel = [algo[n] for n in names]
     algo_bytes = algo_by_kernel[dom]
     achieved = algo_bytes / (ms_avg[dom] / 1e3) / 1e9
+    decode_ms = float(ms_avg.sum())
+    per_kernel = {n: {'ms': float(m), 'algorithmic_bytes': int(a), 'gbps': (a / (m / 1e3) / 1e9) if m > 0 else None,
+                      'frac': (a / (m / 1e3) / 1e9 / peak) if m > 0 else None}
+                  for n, m, a in zip(names, ms_avg, algo_by_kernel)}
     roofline = {'bound': 'hbm', 'kernel': names[dom], 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': NCU_DRAM_BYTES_PER_LAUNCH.get(names[dom]), 'peak_source': peak_src,
                 'traffic_source': NCU_DRAM_SOURCE,
                 'algorithmic_bytes_per_launch': algo_bytes,
                 'kernel_ms': {n: float(m) for n, m in zip(names, ms_avg)},
-                'whole_decode_frac': (payload + rows_pg * ROW_BYTES) / (float(ms_avg.sum()) / 1e3) / 1e9 / peak}
+                'per_kernel': per_kernel,
+                'minimal_bytes_E_plus_D': int(payload + rows_pg * ROW_BYTES),
+                'whole_decode_ms_serialised': decode_ms,
+                'whole_decode_frac': (payload + rows_pg * ROW_BYTES) / (decode_ms / 1e3) / 1e9 / peak}
     del arenas, plans, keep, d
     torch.cuda.empty_cache()
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PST_ABI_VERSION 1
+#define PST_ABI_VERSION 2
 
 typedef struct pst_file pst_file;
 typedef struct pst_plan pst_plan;
@@ -97,8 +97,12 @@ typedef struct pst_plan_info {
     int32_t num_pages;
     int32_t num_columns;
     int32_t num_compressed_pages;
-    int32_t num_index_pages; /* Snappy pages whose 64 KiB fragment boundaries the device has to find (k_snappy_index);
-                                pages made of one literal per block are resolved by the planner */
+    int32_t num_index_pages; /* Snappy pages whose 64 KiB fragment boundaries the device has to find (k_snappy_index) */
+    int32_t num_unwrapped_pages;  /* literal-only Snappy pages (incompressible data): the staging copy drops the framing
+                                     and the device receives them as uncompressed page images */
+    int32_t num_copy_tiles;       /* <= 64 KiB work items of k_copy_tiles (PLAIN fixed-width pages without nulls) */
+    int32_t num_decode_pages;     /* data pages that go through the general page decoder k_decode_pages */
+    int32_t num_snappy_fragments; /* work items of k_snappy_pages */
 } pst_plan_info;
 int pst_plan_get_info(const pst_plan *p, pst_plan_info *out);
 
@@ -112,11 +116,38 @@ typedef struct pst_plan_column {
     int64_t num_values;     /* level entries in the chunk (== rows for flat columns) */
     int64_t values_off;     /* offset in out region: num_values * type_length bytes; BYTE_ARRAY: int64 arena offsets */
     int64_t lens_off;       /* BYTE_ARRAY only: int32 byte lengths[num_values] (else -1) */
-    int64_t valid_off;      /* offset in out region of num_values validity bytes, or -1 when max_def == 0 */
+    int64_t valid_off;      /* offset in out region of num_values validity bytes; -1 when max_def == 0, and for a flat
+                               column whose chunk statistics promise null_count == 0 (the decoder still counts nulls in
+                               d_status[8 + slot]; a non-zero count for such a column means the statistics lied) */
     int64_t rep_off;        /* offset in out region of num_values repetition-level bytes, or -1 when max_rep == 0 */
     int64_t def_off;        /* offset in out region of num_values definition-level bytes (only when max_rep > 0), else -1 */
 } pst_plan_column;
 int pst_plan_get_column(const pst_plan *p, int i, pst_plan_column *out);
+/* Introspection of the plan (host only; used by the CPU tests of the planner and by bench.py's traffic accounting). */
+typedef struct pst_plan_page {
+    int32_t column_slot;    /* plan column the page belongs to */
+    int32_t kind;           /* 0 DATA_PAGE, 2 DICTIONARY_PAGE, 3 DATA_PAGE_V2 */
+    int32_t encoding;       /* parquet Encoding of the values */
+    int32_t codec;          /* codec the DEVICE sees: a literal-only Snappy page is delivered uncompressed (0) */
+    int32_t flags;          /* 1 all-valid (planner read the levels), 2 values go through k_copy_tiles, 4 unwrapped */
+    int32_t stored_bytes;   /* payload bytes in the file */
+    int32_t image_bytes;    /* uncompressed page image bytes */
+    int32_t num_values;
+    int32_t first_value;
+    int32_t fragments;      /* Snappy work items of the page (0 when the device does not decompress it) */
+    int64_t src_off;        /* arena offset of the payload in the raw region */
+    int64_t img_off;        /* arena offset of the page image (== src_off for pages the device sees uncompressed) */
+} pst_plan_page;
+int pst_plan_get_page(const pst_plan *p, int i, pst_plan_page *out);
+typedef struct pst_copy_tile {
+    int64_t src_off;        /* arena offset */
+    int64_t dst_off;        /* out offset */
+    int64_t valid_off;      /* out offset of the validity bytes to set to 1, or -1 */
+    int32_t nbytes;
+    int32_t nvalid;
+} pst_copy_tile;
+int pst_plan_get_copy_tile(const pst_plan *p, int i, pst_copy_tile *out);
+
 /* Host helper: write the raw-region image (page payloads [first_page,last_page) at their planned offsets, plus the
  * tables when first_page == 0) into dst[0:raw_bytes].  Used by the staging threads and by CPU tests of the planner. */
 int pst_plan_fill_raw(const pst_plan *p, uint8_t *dst, int64_t first_page, int64_t last_page);
@@ -134,7 +165,8 @@ int pst_ctx_stats_json(pst_ctx *c, char *buf, size_t cap);
 int pst_plan_upload(pst_ctx *c, pst_plan *p, uint64_t d_arena, uint64_t stream);
 
 /* Enqueue the device decode of a plan whose raw region is resident at d_arena:
- *   K2 snappy -> scratch, K3 RLE/bit-packed levels, K4 PLAIN, K5 dictionary gather, K6 validity.
+ *   K2 snappy -> scratch, value tiles of PLAIN pages without nulls -> out (bulk-copy engine), then for the other
+ *   pages K3 RLE/bit-packed levels, K4 PLAIN, K5 dictionary gather, K6 validity.
  * After the stream reaches this point, `out` holds the columns described by pst_plan_get_column.
  * d_status: device int32[8] {error_code, page, detail, ...} written by the kernels (all zero == ok); the caller
  * zeroes it before the call and checks it after synchronising.  Returns the number of kernels launched in
@@ -144,9 +176,9 @@ int pst_plan_decode(pst_ctx *c, pst_plan *p, uint64_t d_arena, uint64_t d_out, u
 
 /* Measurement aid (bench.py roofline): the same launches with CUDA events between them on `stream`; synchronises and
  * writes the device milliseconds of {snappy fragment index, snappy fragments, snappy serial fallback, byte-array
- * dictionary index, page decode} to ms5[0..4]. */
+ * dictionary index, value tile copy, page decode} to ms6[0..5]. */
 int pst_plan_decode_timed(pst_ctx *c, pst_plan *p, uint64_t d_arena, uint64_t d_out, uint64_t d_status, uint64_t stream,
-                          float *ms5);
+                          float *ms6);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Column post-processing kernels (all async on `stream`; pointers are device addresses).

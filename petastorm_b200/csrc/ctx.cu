@@ -155,6 +155,7 @@ struct PinnedBuf {
 
 struct pst_ctx {
     int device = 0;
+    int sm_count = 148;
     int64_t cache_budget = 0;
     int64_t cache_bytes = 0;
     std::unordered_map<uint64_t, PinnedBuf> cache;
@@ -255,8 +256,10 @@ int pst_ctx_create(int device, int64_t pinned_cache_bytes, int copy_threads, pst
     ck(cudaSetDevice(device), "cudaSetDevice");
     ck(cudaFree(0), "cuda context init");
     ck(configure_decode_kernels(), "configure kernels");
+    ck(configure_copy_kernel(), "configure copy kernel");
     std::unique_ptr<pst_ctx> c(new pst_ctx());
     c->device = device;
+    ck(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device), "SM count");
     c->cache_budget = pinned_cache_bytes;
     if (copy_threads < 0) {
         unsigned hc = std::thread::hardware_concurrency();
@@ -370,6 +373,11 @@ int pst_plan_decode(pst_ctx *c, pst_plan *p, uint64_t d_arena, uint64_t d_out, u
         ck(launch_ba_dict_index(arena, pages, cols, dict, (int)p->ba_dict_pages.size(), status, s), "dict index launch");
         nl++;
     }
+    if (!p->copy_tiles.empty()) {
+        ck(launch_copy_tiles(arena, outp, (const CopyTile *)(arena + p->copy_tiles_off), (int)p->copy_tiles.size(),
+                             c ? c->sm_count : 148, s), "copy tiles launch");
+        nl++;
+    }
     if (!p->data_pages.empty()) {
         ck(launch_decode_pages(arena, outp, cols, pages, data, (int)p->data_pages.size(), status, s), "decode launch");
         nl++;
@@ -385,27 +393,29 @@ int pst_plan_decode(pst_ctx *c, pst_plan *p, uint64_t d_arena, uint64_t d_out, u
 }
 
 // Same launches as pst_plan_decode with a CUDA event between them, on the launching stream; synchronises and reports
-// the device time of each kernel: ms[0..4] = Snappy fragment index, Snappy fragments, Snappy serial fallback,
-// BYTE_ARRAY dictionary index, page decode.  Measurement aid for bench.py's roofline numbers -- not used by the readers.
+// the device time of each kernel: ms[0..5] = Snappy fragment index, Snappy fragments, Snappy serial fallback,
+// BYTE_ARRAY dictionary index, value tile copy, page decode.  Measurement aid for bench.py's roofline numbers -- not used by the readers.
 int pst_plan_decode_timed(pst_ctx *c, pst_plan *p, uint64_t d_arena, uint64_t d_out, uint64_t d_status, uint64_t stream,
-                          float *ms5) {
+                          float *ms6) {
     PST_TRY
-    (void)c;
     cudaStream_t s = (cudaStream_t)stream;
     uint8_t *arena = (uint8_t *)d_arena;
     const DevCol *cols = (const DevCol *)(arena + p->cols_off);
     const DevPage *pages = (const DevPage *)(arena + p->pages_off);
-    cudaEvent_t ev[6];
+    cudaEvent_t ev[7];
     for (auto &e : ev) ck(cudaEventCreate(&e), "cudaEventCreate");
     launch_snappy_stage(p, arena, (int32_t *)d_status, s, ev);
     ck(launch_ba_dict_index(arena, pages, cols, (const int32_t *)(arena + p->dict_list_off),
                             (int)p->ba_dict_pages.size(), (int32_t *)d_status, s), "dict index launch");
     ck(cudaEventRecord(ev[4], s), "record");
+    ck(launch_copy_tiles(arena, (uint8_t *)d_out, (const CopyTile *)(arena + p->copy_tiles_off),
+                         (int)p->copy_tiles.size(), c ? c->sm_count : 148, s), "copy tiles launch");
+    ck(cudaEventRecord(ev[5], s), "record");
     ck(launch_decode_pages(arena, (uint8_t *)d_out, cols, pages, (const int32_t *)(arena + p->data_list_off),
                            (int)p->data_pages.size(), (int32_t *)d_status, s), "decode launch");
-    ck(cudaEventRecord(ev[5], s), "record");
-    ck(cudaEventSynchronize(ev[5]), "sync");
-    for (int i = 0; i < 5; i++) ck(cudaEventElapsedTime(&ms5[i], ev[i], ev[i + 1]), "elapsed");
+    ck(cudaEventRecord(ev[6], s), "record");
+    ck(cudaEventSynchronize(ev[6]), "sync");
+    for (int i = 0; i < 6; i++) ck(cudaEventElapsedTime(&ms6[i], ev[i], ev[i + 1]), "elapsed");
     for (auto &e : ev) cudaEventDestroy(e);
     return 0;
     PST_CATCH(1)

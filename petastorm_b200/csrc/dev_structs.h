@@ -23,6 +23,25 @@ enum DevErr : int32_t {
 
 constexpr int32_t kSnappyFragment = 65536;
 
+// DevPage::flags
+enum PageFlags : uint8_t {
+    PF_ALL_VALID = 1,       // the planner read the definition levels: one RLE run of max_def covering the page
+    PF_COPY = 2,            // PLAIN fixed-width flat all-valid page: its values go to `out` through k_copy_tiles
+    PF_UNWRAPPED = 4,       // stored as literal-only Snappy; the staging copy dropped the framing (device sees NONE)
+};
+
+// One work item of the tile copy kernel: nbytes of value bytes arena[src_off..] -> out[dst_off..], plus `nvalid`
+// validity bytes (value 1) at out[valid_off..] when the column carries a validity array (valid_off >= 0).
+struct CopyTile {
+    int64_t src_off;
+    int64_t dst_off;
+    int64_t valid_off;
+    int32_t nbytes;
+    int32_t nvalid;
+};
+static_assert(sizeof(CopyTile) == 32, "CopyTile must be 32 bytes");
+constexpr int32_t kCopyTileBytes = 65536;
+
 struct SnFrag {             // one work item of the fragment decode kernel
     int32_t page;           // page table index
     int32_t k;              // fragment ordinal inside the page
@@ -44,7 +63,9 @@ struct DevPage {            // 64 bytes
     uint8_t def_enc;        // V1: Enc of definition levels
     uint8_t rep_enc;        // V1: Enc of repetition levels
     uint8_t v2_compressed;  // V2: values section compressed?
-    int32_t page_ordinal;   // ordinal in file order inside the chunk (diagnostics)
+    int16_t page_ordinal;   // ordinal in file order inside the chunk (diagnostics, saturates)
+    uint8_t flags;          // PageFlags (decided by the host planner)
+    uint8_t pad_;
     // Snappy pages: the compressed values are decoded as `nfrag` independent fragments of kSnappyFragment output bytes
     // (the Snappy compressor restarts its match window every 64 KiB, see kernels_decode.cu)
     int32_t frag_first;     // index of this page's first entry in the plan's fragment-position table (nfrag + 1 entries)

@@ -218,11 +218,41 @@ static int level_bits(int max_level) {
     return max_level == 0 ? 0 : b;
 }
 
-// Byte offset of the value section inside the uncompressed image of a V1 data page, or -1 if it cannot be learned
-// from the first bytes of the page.
-static int64_t v1_values_offset(const uint8_t *payload, size_t n, int codec, int max_rep, int max_def, int rep_enc,
-                                int def_enc, int num_values) {
-    if (max_rep == 0 && max_def == 0) return 0;
+// What the planner learns from the first bytes of a data page image: the byte offset of the value section (-1 when it
+// cannot be learned) and whether the definition levels are one RLE run of max_def that covers the page (no nulls).
+struct LevelPeek {
+    int64_t values_off = -1;
+    bool all_valid = false;
+};
+
+// One RLE-hybrid section [p, p+len): true iff it is a single RLE run of `value` covering >= num_values entries
+static bool single_rle_run(const uint8_t *p, size_t len, size_t have, int bit_width, uint32_t value, int64_t num_values) {
+    if (len > have) len = have;
+    size_t q = 0;
+    uint64_t h = 0;
+    for (int shift = 0;; shift += 7) {
+        if (q >= len || shift > 35) return false;
+        const uint8_t b = p[q++];
+        h |= (uint64_t)(b & 0x7f) << shift;
+        if (!(b & 0x80)) break;
+    }
+    if (h & 1) return false;
+    if ((int64_t)(h >> 1) < num_values) return false;
+    const int nb = (bit_width + 7) >> 3;
+    if (q + (size_t)nb > len) return false;
+    uint32_t v = 0;
+    for (int i = 0; i < nb; i++) v |= (uint32_t)p[q + i] << (8 * i);
+    return v == value;
+}
+
+static LevelPeek v1_level_peek(const uint8_t *payload, size_t n, int codec, int max_rep, int max_def, int rep_enc,
+                               int def_enc, int num_values) {
+    LevelPeek r;
+    if (max_rep == 0 && max_def == 0) {
+        r.values_off = 0;
+        r.all_valid = true;
+        return r;
+    }
     uint8_t head[512];
     size_t have;
     if (codec == PST_CODEC_NONE) {
@@ -231,15 +261,19 @@ static int64_t v1_values_offset(const uint8_t *payload, size_t n, int codec, int
     } else if (codec == PST_CODEC_SNAPPY) {
         have = snappy_peek(payload, n, head, sizeof head);
     } else {
-        return -1;
+        return r;
     }
     size_t pos = 0;
-    auto section = [&](int max_level, int enc) -> bool {
+    bool def_single = false;
+    auto section = [&](int max_level, int enc, bool is_def) -> bool {
         if (max_level == 0) return true;
         if (enc == ENC_RLE) {
             if (pos + 4 > have) return false;
             uint32_t len;
             memcpy(&len, head + pos, 4);
+            if (is_def && pos + 4 < have)
+                def_single = single_rle_run(head + pos + 4, len, have - (pos + 4), level_bits(max_level),
+                                            (uint32_t)max_level, num_values);
             pos += 4 + (size_t)len;
             return true;
         }
@@ -249,16 +283,21 @@ static int64_t v1_values_offset(const uint8_t *payload, size_t n, int codec, int
         }
         return false;
     };
-    if (!section(max_rep, rep_enc)) return -1;
-    if (pos > have && max_def > 0 && def_enc == ENC_RLE) return -1;  // cannot see the def length prefix
-    if (!section(max_def, def_enc)) return -1;
-    return (int64_t)pos;
+    if (!section(max_rep, rep_enc, false)) return r;
+    if (pos > have && max_def > 0 && def_enc == ENC_RLE) return r;  // cannot see the def length prefix
+    if (!section(max_def, def_enc, true)) return r;
+    r.values_off = (int64_t)pos;
+    r.all_valid = max_def == 0 || def_single;
+    return r;
 }
 
-// Incompressible data leaves the Snappy compressor as one literal element per 64 KiB block.  Such a stream needs no
-// device-side index: the fragment boundaries are read off the (few) tag bytes right here.  Returns false for anything
-// else; pos[0..nfrag] receives the compressed offsets (same convention as k_snappy_index).
-static bool literal_only_fragments(const uint8_t *s, int64_t n, int64_t ulen, int nfrag, uint32_t *pos) {
+// Incompressible data leaves the Snappy compressor as literal elements only (one per 64 KiB block).  Such a stream is
+// not compressed at all, just framed: the planner records where the literal bytes lie in the file and the staging copy
+// (pst_plan_fill_raw) lays them down back to back, so the device receives an ordinary uncompressed page image and no
+// Snappy work item exists for the page.  Returns false for a stream with any back-reference (or an unreasonable number
+// of literals); segs receives {offset inside s, length} of every literal.
+static bool literal_segments(const uint8_t *s, int64_t n, int64_t ulen, std::vector<std::pair<int64_t, int32_t>> &segs) {
+    constexpr size_t kMaxSegs = 64;
     int64_t ip = 0;
     uint64_t v = 0;
     for (int shift = 0;; shift += 7) {
@@ -269,11 +308,7 @@ static bool literal_only_fragments(const uint8_t *s, int64_t n, int64_t ulen, in
     }
     if ((int64_t)v != ulen) return false;
     int64_t op = 0;
-    pos[0] = 0;
-    for (int k = 0; k < nfrag; k++) {
-        if (k > 0) pos[k] = (uint32_t)ip;
-        const int64_t want = std::min<int64_t>(kSnappyFragment, ulen - op);
-        if (ip >= n) return false;
+    while (ip < n) {
         const uint8_t tag = s[ip];
         if ((tag & 3) != 0) return false;
         const int t6 = tag >> 2;
@@ -289,14 +324,12 @@ static bool literal_only_fragments(const uint8_t *s, int64_t n, int64_t ulen, in
             len += 1;
             hdr = 1 + nb;
         }
-        if (len != want) return false;
+        if (len > ulen - op || ip + hdr + len > n || segs.size() >= kMaxSegs) return false;
+        segs.emplace_back(ip + hdr, (int32_t)len);
         ip += hdr + len;
         op += len;
-        if (ip > n) return false;
     }
-    if (ip != n || op != ulen) return false;
-    pos[nfrag] = (uint32_t)n;
-    return true;
+    return op == ulen;
 }
 
 int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_plan **out) {
@@ -316,6 +349,7 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
     int64_t scratch_cur = 0;  // cursor inside the scratch region (relative; rebased after raw size is known)
     std::vector<int64_t> scratch_rel;  // per page: relative scratch offset or -1
     std::vector<int64_t> dict_index_rel(ncols, -1);
+    std::vector<char> stats_no_nulls(ncols, 0);   // the chunk statistics promise null_count == 0
 
     for (int slot = 0; slot < ncols; slot++) {
         int col = cols[slot];
@@ -346,6 +380,7 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
         dc.dict_page = -1;
         dc.dict_index_off = -1;
         dc.values_off = dc.valid_off = dc.rep_off = dc.def_off = dc.lens_off = -1;
+        stats_no_nulls[slot] = c.has_null_count && c.null_count == 0;
 
         int64_t off = c.start_offset();
         int64_t chunk_end = off + c.total_compressed_size;
@@ -372,9 +407,10 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
             d.col = (int16_t)slot;
             d.encoding = (uint8_t)h.encoding;
             d.codec = (uint8_t)c.codec;
-            d.page_ordinal = ordinal++;
+            d.page_ordinal = (int16_t)std::min(ordinal++, 32767);
             d.def_bytes = d.rep_bytes = -1;
             int64_t values_off_in_image = -1;
+            bool all_valid = false;
             if (h.type == 2) {
                 d.kind = PK_DICT;
                 if (h.encoding != ENC_PLAIN && h.encoding != ENC_PLAIN_DICTIONARY)
@@ -389,9 +425,10 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
                 d.rep_enc = (uint8_t)h.rep_encoding;
                 d.first_value = (int32_t)seen;
                 seen += h.num_values;
-                values_off_in_image = v1_values_offset(f->map + payload, (size_t)h.compressed_page_size, c.codec,
-                                                       leaf.max_rep, leaf.max_def, h.rep_encoding, h.def_encoding,
-                                                       h.num_values);
+                const LevelPeek lp = v1_level_peek(f->map + payload, (size_t)h.compressed_page_size, c.codec, leaf.max_rep,
+                                                   leaf.max_def, h.rep_encoding, h.def_encoding, h.num_values);
+                values_off_in_image = lp.values_off;
+                all_valid = lp.all_valid;
             } else if (h.type == 3) {
                 d.kind = PK_DATA_V2;
                 d.def_bytes = h.def_bytes;
@@ -400,7 +437,13 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
                 d.first_value = (int32_t)seen;
                 seen += h.num_values;
                 values_off_in_image = (int64_t)h.def_bytes + h.rep_bytes;
+                if (values_off_in_image > h.compressed_page_size || values_off_in_image > h.uncompressed_page_size)
+                    throw std::runtime_error("V2 page level sections exceed the page size");
                 if (!h.is_compressed) d.codec = PST_CODEC_NONE;
+                all_valid = leaf.max_def == 0 ||
+                            (h.num_nulls == 0 && h.def_bytes > 0 &&
+                             single_rle_run(f->map + payload + h.rep_bytes, (size_t)h.def_bytes, (size_t)h.def_bytes,
+                                            level_bits(leaf.max_def), (uint32_t)leaf.max_def, h.num_values));
             } else {
                 throw std::runtime_error("unknown page type " + std::to_string(h.type));
             }
@@ -414,11 +457,28 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
                         throw std::runtime_error("unsupported value encoding " + std::to_string(h.encoding) +
                                                  " in column " + se.name);
                 }
+                if (all_valid) d.flags |= PF_ALL_VALID;
             }
             // placement: payload as stored goes into raw; phase chosen so the value section is 16B aligned
             int64_t phase = 0;
             if (values_off_in_image > 0) phase = (16 - values_off_in_image % 16) % 16;
+            hp.stored_size = h.compressed_page_size;
             bool compressed = d.codec != PST_CODEC_NONE && d.comp_size > 0;
+            if (compressed && d.codec == PST_CODEC_SNAPPY) {
+                // the compressed stream covers the whole image (V1) or everything behind the level bytes (V2)
+                const int64_t lv = d.kind == PK_DATA_V2 ? (int64_t)d.def_bytes + d.rep_bytes : 0;
+                std::vector<std::pair<int64_t, int32_t>> segs;
+                if (literal_segments(f->map + payload + lv, (int64_t)d.comp_size - lv, (int64_t)d.uncomp_size - lv, segs)) {
+                    // framed, not compressed: the staging copy lays the literal bytes down back to back
+                    if (lv > 0) hp.segs.emplace_back(payload, (int32_t)lv);
+                    for (const auto &sg : segs) hp.segs.emplace_back(payload + lv + sg.first, sg.second);
+                    d.codec = PST_CODEC_NONE;
+                    d.comp_size = d.uncomp_size;
+                    d.flags |= PF_UNWRAPPED;
+                    compressed = false;
+                    p->unwrapped_pages++;
+                }
+            }
             if (compressed) {
                 d.src_off = align_up(raw_cur, 16);
                 raw_cur = d.src_off + d.comp_size;
@@ -429,7 +489,6 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
                     p->gzip_pages.push_back((int32_t)p->pages.size());
                 } else {
                     p->compressed_pages.push_back((int32_t)p->pages.size());
-                    // the compressed stream covers the whole image (V1) or everything behind the level bytes (V2)
                     const int64_t values_uncomp = (int64_t)d.uncomp_size -
                                                   (d.kind == PK_DATA_V2 ? (int64_t)d.def_bytes + d.rep_bytes : 0);
                     d.nfrag = (int32_t)std::max<int64_t>(1, (values_uncomp + kSnappyFragment - 1) / kSnappyFragment);
@@ -439,10 +498,7 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
                     if (d.nfrag > 1) {
                         d.multi_slot = (int32_t)p->multi_pages.size();
                         p->multi_pages.push_back((int32_t)p->pages.size());
-                        const int64_t lv = (int64_t)d.uncomp_size - values_uncomp;   // V2: uncompressed level bytes
-                        if (!literal_only_fragments(f->map + payload + lv, (int64_t)d.comp_size - lv, values_uncomp, d.nfrag,
-                                                    p->frag_pos_host.data() + d.frag_first))
-                            p->index_pages.push_back((int32_t)p->pages.size());
+                        p->index_pages.push_back((int32_t)p->pages.size());
                     }
                     for (int32_t k = 0; k < d.nfrag; k++)
                         p->snappy_frags.push_back(SnFrag{(int32_t)p->pages.size(), k});
@@ -453,8 +509,17 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
                 d.img_off = d.src_off;
                 scratch_rel.push_back(-1);
             }
-            if (d.kind != PK_DICT) p->data_pages.push_back((int32_t)p->pages.size());
-            p->payload_bytes += d.comp_size;
+            // PLAIN fixed-width values of a flat page without nulls are a plain byte range of the page image: they go
+            // to `out` through the tile copy kernel (k_copy_tiles) instead of the general page decoder
+            hp.copy_v0 = -1;
+            if (d.kind != PK_DICT && all_valid && values_off_in_image >= 0 && h.encoding == ENC_PLAIN &&
+                leaf.max_rep == 0 && dc.width > 0 && c.type != PST_BOOLEAN && d.codec != PST_CODEC_GZIP &&
+                values_off_in_image + (int64_t)h.num_values * dc.width <= (int64_t)d.uncomp_size) {
+                hp.copy_v0 = values_off_in_image;
+                d.flags |= PF_COPY;
+            }
+            if (d.kind != PK_DICT && !(d.flags & PF_COPY)) p->data_pages.push_back((int32_t)p->pages.size());
+            p->payload_bytes += hp.stored_size;
             p->uncompressed_bytes += d.uncomp_size;
             p->pages.push_back(hp);
         }
@@ -495,7 +560,15 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
     p->index_list_off = align_up(p->gzip_list_off + 4 * (int64_t)p->gzip_pages.size(), 16);
     // fragment positions (host-filled for literal-only pages, written by k_snappy_index for the others) and page flags
     // (zero; raised on the device): part of the raw image so that every upload resets them
-    p->frag_pos_off = align_up(p->index_list_off + 4 * (int64_t)p->index_pages.size(), 16);
+    p->copy_tiles_off = align_up(p->index_list_off + 4 * (int64_t)p->index_pages.size(), 32);
+    // (the tile list itself is built below, once the out layout is known; its size only depends on the pages)
+    int64_t n_tiles = 0;
+    for (const HostPage &hp : p->pages)
+        if (hp.copy_v0 >= 0) {
+            const int64_t w = p->dcols[hp.d.col].width, per = (kCopyTileBytes / w) * w;
+            n_tiles += ((int64_t)hp.d.num_values * w + per - 1) / per;
+        }
+    p->frag_pos_off = align_up(p->copy_tiles_off + (int64_t)sizeof(CopyTile) * n_tiles, 16);
     p->page_flag_off = align_up(p->frag_pos_off + 4 * p->frag_pos_count, 16);
     p->raw_bytes = align_up(p->page_flag_off + 4 * (int64_t)p->multi_pages.size(), 256);
     p->scratch_off = p->raw_bytes;
@@ -521,7 +594,9 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
         } else {
             out_cur += (int64_t)dc.width * n;
         }
-        if (dc.max_def > 0) {
+        // A flat column whose chunk statistics say null_count == 0 carries no validity array: every page is all-valid
+        // (the page decoder still counts level entries below max_def, and the host raises if the statistics lied).
+        if (dc.max_def > 0 && !(stats_no_nulls[slot] && dc.max_rep == 0)) {
             out_cur = align_up(out_cur, 256);
             dc.valid_off = out_cur;
             out_cur += n;
@@ -536,6 +611,23 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
         }
     }
     p->out_bytes = align_up(out_cur + 16, 256);
+
+    // ---- tile list of the copy kernel
+    for (const HostPage &hp : p->pages) {
+        if (hp.copy_v0 < 0) continue;
+        const DevCol &dc = p->dcols[hp.d.col];
+        const int64_t w = dc.width, per = (kCopyTileBytes / w) * w, total = (int64_t)hp.d.num_values * w;
+        for (int64_t a = 0; a < total; a += per) {
+            CopyTile t;
+            t.src_off = hp.d.img_off + hp.copy_v0 + a;
+            t.dst_off = dc.values_off + (int64_t)hp.d.first_value * w + a;
+            t.nbytes = (int32_t)std::min(per, total - a);
+            t.valid_off = dc.valid_off >= 0 ? dc.valid_off + hp.d.first_value + a / w : -1;
+            t.nvalid = dc.valid_off >= 0 ? t.nbytes / (int32_t)w : 0;
+            p->copy_tiles.push_back(t);
+        }
+    }
+    if ((int64_t)p->copy_tiles.size() != n_tiles) throw std::runtime_error("internal error: copy tile count");
 
     // ---- host image of the tables
     p->tables.assign((size_t)(p->raw_bytes - p->tables_off), 0);
@@ -557,6 +649,8 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
         memcpy(t + (p->gzip_list_off - p->tables_off), p->gzip_pages.data(), 4 * p->gzip_pages.size());
     if (!p->index_pages.empty())
         memcpy(t + (p->index_list_off - p->tables_off), p->index_pages.data(), 4 * p->index_pages.size());
+    if (!p->copy_tiles.empty())
+        memcpy(t + (p->copy_tiles_off - p->tables_off), p->copy_tiles.data(), sizeof(CopyTile) * p->copy_tiles.size());
     if (!p->frag_pos_host.empty())
         memcpy(t + (p->frag_pos_off - p->tables_off), p->frag_pos_host.data(), 4 * p->frag_pos_host.size());
 
@@ -593,6 +687,10 @@ int pst_plan_get_info(const pst_plan *p, pst_plan_info *out) {
     out->num_columns = (int32_t)p->cols.size();
     out->num_compressed_pages = (int32_t)(p->compressed_pages.size() + p->gzip_pages.size());
     out->num_index_pages = (int32_t)p->index_pages.size();
+    out->num_unwrapped_pages = (int32_t)p->unwrapped_pages;
+    out->num_copy_tiles = (int32_t)p->copy_tiles.size();
+    out->num_decode_pages = (int32_t)p->data_pages.size();
+    out->num_snappy_fragments = (int32_t)p->snappy_frags.size();
     return 0;
 }
 
@@ -617,6 +715,41 @@ int pst_plan_get_column(const pst_plan *p, int i, pst_plan_column *out) {
     return 0;
 }
 
+int pst_plan_get_page(const pst_plan *p, int i, pst_plan_page *out) {
+    if (i < 0 || i >= (int)p->pages.size()) {
+        set_error("plan page out of range");
+        return 1;
+    }
+    const HostPage &hp = p->pages[i];
+    out->column_slot = hp.d.col;
+    out->kind = hp.d.kind;
+    out->encoding = hp.d.encoding;
+    out->codec = hp.d.codec;
+    out->flags = hp.d.flags;
+    out->stored_bytes = hp.stored_size;
+    out->image_bytes = hp.d.uncomp_size;
+    out->num_values = hp.d.num_values;
+    out->first_value = hp.d.first_value;
+    out->fragments = hp.d.nfrag;
+    out->src_off = hp.d.src_off;
+    out->img_off = hp.d.img_off;
+    return 0;
+}
+
+int pst_plan_get_copy_tile(const pst_plan *p, int i, pst_copy_tile *out) {
+    if (i < 0 || i >= (int)p->copy_tiles.size()) {
+        set_error("copy tile out of range");
+        return 1;
+    }
+    const CopyTile &t = p->copy_tiles[i];
+    out->src_off = t.src_off;
+    out->dst_off = t.dst_off;
+    out->valid_off = t.valid_off;
+    out->nbytes = t.nbytes;
+    out->nvalid = t.nvalid;
+    return 0;
+}
+
 // Copies the plan's raw region image (payloads at their planned offsets + tables) into `dst` (raw_bytes bytes).
 // Host-only helper used by the staging path and by CPU tests of the planner.
 int pst_plan_fill_raw(const pst_plan *p, uint8_t *dst, int64_t first_page, int64_t last_page) {
@@ -625,7 +758,15 @@ int pst_plan_fill_raw(const pst_plan *p, uint8_t *dst, int64_t first_page, int64
     if (last_page > n) last_page = n;
     for (int64_t i = first_page; i < last_page; i++) {
         const HostPage &hp = p->pages[i];
-        memcpy(dst + hp.d.src_off, p->file->map + hp.file_off, (size_t)hp.d.comp_size);
+        if (hp.segs.empty()) {
+            memcpy(dst + hp.d.src_off, p->file->map + hp.file_off, (size_t)hp.d.comp_size);
+        } else {   // literal-only Snappy page: the literal bytes back to back = the uncompressed page image
+            uint8_t *o = dst + hp.d.src_off;
+            for (const auto &sg : hp.segs) {
+                memcpy(o, p->file->map + sg.first, (size_t)sg.second);
+                o += sg.second;
+            }
+        }
     }
     if (first_page == 0) memcpy(dst + p->tables_off, p->tables.data(), p->tables.size());
     return 0;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "dev_structs.h"
@@ -20,6 +21,10 @@ struct pst_file {
 struct HostPage {
     pst::DevPage d;          // what the device sees
     int64_t file_off = 0;    // payload position in the file
+    int32_t stored_size = 0; // payload bytes as stored in the file
+    int64_t copy_v0 = -1;    // >= 0: PF_COPY page, byte offset of the value section inside the page image
+    // literal-only Snappy page (PF_UNWRAPPED): {file offset, length} of the byte ranges that make up the page image
+    std::vector<std::pair<int64_t, int32_t>> segs;
 };
 
 struct pst_plan {
@@ -35,6 +40,9 @@ struct pst_plan {
     std::vector<int32_t> multi_pages;        // compressed pages with more than one fragment (indexed first)
     std::vector<int32_t> gzip_pages;         // page indices compressed with GZIP
     std::vector<int32_t> index_pages;        // multi-fragment pages whose fragment positions the device has to find
+    std::vector<pst::CopyTile> copy_tiles;   // work items of k_copy_tiles (PF_COPY pages, <= 64 KiB each)
+    int64_t unwrapped_pages = 0;             // literal-only Snappy pages delivered as uncompressed images
+    int64_t copy_tiles_off = 0;
     std::vector<uint32_t> frag_pos_host;     // fragment-position table as far as the host knows it (literal-only pages)
     int64_t frag_pos_count = 0;              // entries of the fragment-position table (sum of nfrag + 1)
     int64_t num_rows = 0;

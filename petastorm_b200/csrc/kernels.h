@@ -29,6 +29,11 @@ cudaError_t launch_ba_dict_index(uint8_t *arena, const DevPage *pages, const Dev
 cudaError_t launch_decode_pages(uint8_t *arena, uint8_t *out, const DevCol *cols, const DevPage *pages,
                                 const int32_t *list, int n, int32_t *status, cudaStream_t s);
 
+// ---- kernels_copy.cu: PLAIN value tiles -> out with the bulk-copy engine (cp.async.bulk + mbarrier)
+cudaError_t configure_copy_kernel();
+cudaError_t launch_copy_tiles(const uint8_t *arena, uint8_t *out, const CopyTile *tiles, int n_tiles, int sm_count,
+                              cudaStream_t s);
+
 // ---- kernels_ops.cu
 cudaError_t launch_nullable_to_f64(const void *values, const uint8_t *valid, int64_t n, int ptype, int bits,
                                    int is_unsigned, double *out, cudaStream_t s);

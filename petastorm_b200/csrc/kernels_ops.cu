@@ -161,8 +161,35 @@ cudaError_t launch_gather_rows(const uint8_t *src, const int64_t *idx, int64_t n
                                cudaStream_t s) {
     return gather_impl(src, idx, n_out, row_bytes, row_bytes, dst, s);
 }
+// NGram windows over a scalar column (rows of 1..16 bytes): one thread per (window, timestep) element.  Consecutive
+// threads write consecutive elements of `dst` and read consecutive rows of `src` (windows of neighbouring starts
+// overlap), so both sides coalesce; a CTA-per-window copy would move 64 bytes per warp.
+template <typename T>
+__global__ void k_ngram_small(const T *__restrict__ src, const int64_t *__restrict__ starts, int64_t n_windows,
+                              int length, T *__restrict__ dst) {
+    const int64_t total = n_windows * (int64_t)length;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t w = i / length;
+        const int t = (int)(i - w * length);
+        dst[i] = src[starts[w] + t];
+    }
+}
+
 cudaError_t launch_ngram_gather(const uint8_t *src, const int64_t *starts, int64_t n_windows, int length,
                                 int64_t row_bytes, uint8_t *dst, cudaStream_t s) {
+    if (n_windows <= 0 || length <= 0 || row_bytes <= 0) return cudaSuccess;
+    const bool aligned = (((uintptr_t)src | (uintptr_t)dst) & (uintptr_t)(row_bytes - 1)) == 0;
+    if (aligned && (row_bytes == 1 || row_bytes == 2 || row_bytes == 4 || row_bytes == 8 || row_bytes == 16)) {
+        const int g = grid_for(n_windows * (int64_t)length, kThreads);
+        switch (row_bytes) {
+            case 1: k_ngram_small<uint8_t><<<g, kThreads, 0, s>>>((const uint8_t *)src, starts, n_windows, length, (uint8_t *)dst); break;
+            case 2: k_ngram_small<uint16_t><<<g, kThreads, 0, s>>>((const uint16_t *)src, starts, n_windows, length, (uint16_t *)dst); break;
+            case 4: k_ngram_small<uint32_t><<<g, kThreads, 0, s>>>((const uint32_t *)src, starts, n_windows, length, (uint32_t *)dst); break;
+            case 8: k_ngram_small<uint64_t><<<g, kThreads, 0, s>>>((const uint64_t *)src, starts, n_windows, length, (uint64_t *)dst); break;
+            default: k_ngram_small<uint4><<<g, kThreads, 0, s>>>((const uint4 *)src, starts, n_windows, length, (uint4 *)dst); break;
+        }
+        return cudaGetLastError();
+    }
     return gather_impl(src, starts, n_windows, row_bytes, row_bytes * length, dst, s);
 }
 

@@ -232,7 +232,7 @@ class _GpuWorkerBase(WorkerBase):
         value = raw.partition_values[name]
         if dtype is np.int64:
             return np.full(count, int(value), dtype=np.int64)
-        return np.full(count, value, dtype=np.str_)
+        return np.full(count, str(value))      # numpy infers the string width (dtype=np.str_ alone would mean '<U1')
 
     @staticmethod
     def _leaf_of(raw, name):
@@ -339,18 +339,43 @@ class GpuArrowResultsQueueReader(object):
 
     def __init__(self, output='torch'):
         self._output = output
+        self._peeked = None
 
     @property
     def batched_output(self):
         return True
 
+    def _next_batch(self, workers_pool):
+        if self._peeked is not None:
+            batch, self._peeked = self._peeked, None
+            return batch
+        batch = workers_pool.get_results()
+        if isinstance(batch, PendingRowGroup):
+            batch = batch.resolve()
+        batch.wait()
+        return batch
+
+    def peek_rowgroup(self, workers_pool):
+        """Columns of the next row-group without consuming it (the loaders look at the value types to pick the
+        device-batched path); None at the end of the data."""
+        try:
+            if self._peeked is None:
+                self._peeked = self._next_batch(workers_pool)
+            return self._peeked.columns
+        except EmptyResultError:
+            return None
+
+    def read_next_rowgroup(self, workers_pool, raw=False):
+        """Whole next row-group as ``{field: column}`` - entry point of the device-batched loaders."""
+        try:
+            return dict(self._next_batch(workers_pool).columns)
+        except EmptyResultError:
+            raise StopIteration
+
     def read_next(self, workers_pool, schema, ngram):
         try:
             assert not ngram, 'ArrowReader does not support ngrams for now'
-            batch = workers_pool.get_results()
-            if isinstance(batch, PendingRowGroup):
-                batch = batch.resolve()
-            batch.wait()
+            batch = self._next_batch(workers_pool)
             cols = batch.columns
             if self._output == 'numpy':
                 cols = {k: _npify(v) for k, v in cols.items()}
@@ -636,17 +661,53 @@ class GpuRowGroupRows(object):
         return out
 
 
+class NGramColumns(dict):
+    """Windows of one row-group in device form: ``self[name]`` is a tensor ``[W, L, ...]`` (window, timestep, value
+    shape) for every field of the NGram; ``timesteps`` maps each offset of the NGram to the field names it carries
+    (petastorm/ngram.py:259-264 projects each timestep to its own field list)."""
+
+    def __init__(self, columns, timesteps):
+        super(NGramColumns, self).__init__(columns)
+        self.timesteps = timesteps
+
+
 class GpuNGramWindows(object):
     """NGram result of one row-group: window starts + the per-row columns they index into."""
 
-    def __init__(self, rows, starts, ngram):
+    def __init__(self, rows, starts, ngram, starts_dev=None):
         self.rows = rows
         self.starts = starts          # python list of start rows
+        self.starts_dev = starts_dev  # the same as a CUDA int64 tensor (None when the windows were formed on the host)
         self.ngram = ngram
         self.num_rows = len(starts)
 
     def wait(self):
         self.rows.wait()
+
+    def window_columns(self, first=0):
+        """:class:`NGramColumns` of the windows ``first:`` - one window-gather kernel (``pst_ngram_gather``) per field,
+        or None when a field has no tensor form (strings, nulls, ragged arrays)."""
+        ng = self.ngram
+        base = ng.base_key
+        timesteps = {base + k: ng.get_field_names_at_timestep(base + k) for k in range(ng.length)}
+        names = [n for n in self.rows.columns if any(n in f for f in timesteps.values())]
+        cols = {}
+        for name in names:
+            v = self.rows.columns[name]
+            t = v.tensor if isinstance(v, ScalarColumn) else v
+            if not isinstance(t, torch.Tensor):
+                return None
+            cols[name] = t
+        starts = self.starts_dev
+        if starts is None:
+            device = next(iter(cols.values())).device if cols else None
+            starts = torch.tensor(self.starts, dtype=torch.int64, device=device)
+        else:
+            starts.record_stream(torch.cuda.current_stream(starts.device))   # allocated on the worker's side stream
+        if first:
+            starts = starts[first:]
+        return NGramColumns({name: device_ops.ngram_gather(t.contiguous(), starts, ng.length)
+                             for name, t in cols.items()}, timesteps)
 
 
 class GpuPyDictResultsQueueReader(object):
@@ -676,19 +737,41 @@ class GpuPyDictResultsQueueReader(object):
             group.wait()
             return group
 
-    def read_next_rowgroup(self, workers_pool):
+    def peek_rowgroup(self, workers_pool):
+        """Columns of the (rest of the) current row-group without consuming it: ``{field: column}`` for plain rows,
+        the :class:`GpuNGramWindows` for an NGram reader; None at the end of the data."""
+        try:
+            with self._lock:
+                while self._current is None or self._next_index >= self._current.num_rows:
+                    self._current = self._next_group(workers_pool)
+                    self._next_index = 0
+                return self._current if isinstance(self._current, GpuNGramWindows) else self._current.columns
+        except EmptyResultError:
+            return None
+
+    def read_next_rowgroup(self, workers_pool, raw=False):
         """Whole (rest of the) current row-group as ``{field: column}`` with device tensors where they exist - the
-        entry point of the batched loaders (no per-row namedtuples)."""
+        entry point of the device-batched loaders (no per-row namedtuples).  An NGram reader hands out
+        :class:`NGramColumns` (``[W, L, ...]`` per field), or the :class:`GpuNGramWindows` itself when a field has no
+        tensor form.  ``raw=True`` keeps :class:`ScalarColumn` wrappers (per-row numpy scalars on demand)."""
         try:
             with self._lock:
                 if self._current is not None and self._next_index < self._current.num_rows:
                     cur, start = self._current, self._next_index
-                    self._current = None
-                    cols = {k: v[start:] for k, v in cur.columns.items()}
                 else:
-                    cur = self._next_group(workers_pool)
-                    self._current = None
-                    cols = dict(cur.columns)
+                    cur, start = self._next_group(workers_pool), 0
+                self._current = None
+            if isinstance(cur, GpuNGramWindows):
+                cols = cur.window_columns(start)
+                if cols is None:
+                    # hand the group back: the caller walks it window by window through read_next
+                    with self._lock:
+                        self._current, self._next_index = cur, start
+                    return cur
+                return cols
+            cols = {k: (v[start:] if start else v) for k, v in cur.columns.items()}
+            if raw:
+                return cols
             return {k: (v.tensor if isinstance(v, ScalarColumn) else v) for k, v in cols.items()}
         except EmptyResultError:
             raise StopIteration
@@ -1082,22 +1165,29 @@ class GpuPyDictWorker(_GpuWorkerBase):
 
     # ---- NGram --------------------------------------------------------------------------------------------------
     def _form_ngram(self, rows):
+        """Window starts of a decoded row-group (petastorm/ngram.py:225-270).  The timestamp column was produced on the
+        post-processing stream, so the validity kernel and the compaction run there too."""
         ts_name = self._ngram.timestamp_field.name
         ts = rows.columns[ts_name]
         if isinstance(ts, ScalarColumn):
             ts = ts.tensor
+        device = self._get_decoder().device
+        if self._post_stream is None:
+            self._post_stream = torch.cuda.Stream(device)
         ts_list = [_npify(v) for v in ts] if not isinstance(ts, torch.Tensor) else None
-        if ts_list is not None and len(ts_list) and isinstance(ts_list[0], (np.integer, int)) and \
-                all(v is not None for v in ts_list):
-            ts_dev = torch.tensor(np.asarray(ts_list, dtype=np.int64), device=self._get_decoder().device)
-            with torch.cuda.stream(self._get_decoder().stream):
-                starts = self._ngram.window_starts_device(ts_dev).cpu().tolist()
-        elif isinstance(ts, torch.Tensor) and not ts.is_floating_point():
-            with torch.cuda.stream(self._get_decoder().stream):
-                starts = self._ngram.window_starts_device(ts.to(torch.int64)).cpu().tolist()
-        else:
+        starts_dev = None
+        with torch.cuda.stream(self._post_stream):
+            if ts_list is not None and len(ts_list) and isinstance(ts_list[0], (np.integer, int)) and \
+                    all(v is not None for v in ts_list):
+                ts_dev = torch.tensor(np.asarray(ts_list, dtype=np.int64), device=device)
+                starts_dev = self._ngram.window_starts_device(ts_dev)
+            elif isinstance(ts, torch.Tensor) and not ts.is_floating_point():
+                starts_dev = self._ngram.window_starts_device(ts.to(torch.int64))
+            if starts_dev is not None:
+                starts = starts_dev.cpu().tolist()
+        if starts_dev is None:
             starts = self._ngram.window_starts_host(ts_list if ts_list is not None else list(ts.cpu().numpy()))
-        return GpuNGramWindows(rows, starts, self._ngram)
+        return GpuNGramWindows(rows, starts, self._ngram, starts_dev)
 
 
 def _npy_header_len(prefix):

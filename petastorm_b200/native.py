@@ -42,13 +42,26 @@ class ChunkInfo(Structure):
 class PlanInfo(Structure):
     _fields_ = [('num_rows', c_int64), ('raw_bytes', c_int64), ('arena_bytes', c_int64), ('out_bytes', c_int64),
                 ('payload_bytes', c_int64), ('uncompressed_bytes', c_int64), ('num_pages', c_int32),
-                ('num_columns', c_int32), ('num_compressed_pages', c_int32), ('num_index_pages', c_int32)]
+                ('num_columns', c_int32), ('num_compressed_pages', c_int32), ('num_index_pages', c_int32),
+                ('num_unwrapped_pages', c_int32), ('num_copy_tiles', c_int32), ('num_decode_pages', c_int32),
+                ('num_snappy_fragments', c_int32)]
 
 
 class PlanColumn(Structure):
     _fields_ = [('column', c_int32), ('physical_type', c_int32), ('type_length', c_int32), ('max_def', c_int32),
                 ('max_rep', c_int32), ('has_dictionary', c_int32), ('num_values', c_int64), ('values_off', c_int64),
                 ('lens_off', c_int64), ('valid_off', c_int64), ('rep_off', c_int64), ('def_off', c_int64)]
+
+
+class PlanPage(Structure):
+    _fields_ = [('column_slot', c_int32), ('kind', c_int32), ('encoding', c_int32), ('codec', c_int32),
+                ('flags', c_int32), ('stored_bytes', c_int32), ('image_bytes', c_int32), ('num_values', c_int32),
+                ('first_value', c_int32), ('fragments', c_int32), ('src_off', c_int64), ('img_off', c_int64)]
+
+
+class CopyTile(Structure):
+    _fields_ = [('src_off', c_int64), ('dst_off', c_int64), ('valid_off', c_int64), ('nbytes', c_int32),
+                ('nvalid', c_int32)]
 
 
 def _sig(name, restype, *argtypes):
@@ -78,6 +91,8 @@ _sig('pst_plan_destroy', None, c_void_p)
 _sig('pst_plan_get_info', c_int, c_void_p, POINTER(PlanInfo))
 _sig('pst_plan_get_column', c_int, c_void_p, c_int, POINTER(PlanColumn))
 _sig('pst_plan_fill_raw', c_int, c_void_p, c_void_p, c_int64, c_int64)
+_sig('pst_plan_get_page', c_int, c_void_p, c_int, POINTER(PlanPage))
+_sig('pst_plan_get_copy_tile', c_int, c_void_p, c_int, POINTER(CopyTile))
 _sig('pst_ctx_create', c_int, c_int, c_int64, c_int, POINTER(c_void_p))
 _sig('pst_ctx_destroy', None, c_void_p)
 _sig('pst_ctx_stats_json', c_int, c_void_p, c_char_p, c_size_t)
@@ -113,6 +128,7 @@ EXPORTED = [
     'pst_file_num_row_groups', 'pst_file_num_rows', 'pst_file_row_group_num_rows', 'pst_file_num_columns',
     'pst_file_schema_json', 'pst_file_kv_metadata', 'pst_file_num_kv', 'pst_file_kv_at', 'pst_file_chunk_info',
     'pst_plan_create', 'pst_plan_destroy', 'pst_plan_get_info', 'pst_plan_get_column', 'pst_plan_fill_raw',
+    'pst_plan_get_page', 'pst_plan_get_copy_tile',
     'pst_ctx_create', 'pst_ctx_destroy', 'pst_ctx_stats_json', 'pst_plan_upload', 'pst_plan_decode', 'pst_plan_decode_timed',
     'pst_nullable_to_f64', 'pst_narrow_int32', 'pst_gather_rows', 'pst_npy_batch', 'pst_blob_prefix', 'pst_zip_inflate_batch', 'pst_png_work_bytes',
     'pst_png_batch', 'pst_jpeg_available', 'pst_jpeg_backend', 'pst_jpeg_batch', 'pst_mask_in_set_i64',
@@ -199,6 +215,16 @@ class Plan(object):
     @property
     def handle(self):
         return self._h
+
+    def page(self, i):
+        pg = PlanPage()
+        check(lib.pst_plan_get_page(self._h, i, byref(pg)))
+        return pg
+
+    def copy_tile(self, i):
+        t = CopyTile()
+        check(lib.pst_plan_get_copy_tile(self._h, i, byref(t)))
+        return t
 
     def fill_raw(self, buf_address):
         check(lib.pst_plan_fill_raw(self._h, c_void_p(buf_address), 0, 1 << 62))

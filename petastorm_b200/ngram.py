@@ -86,6 +86,10 @@ class NGram(object):
     def get_field_names_at_all_timesteps(self):
         return list({f for fields in self._fields.values() for f in fields})
 
+    def get_field_names_at_all_timesteps_names(self):
+        """Names (not field objects) of every field that appears at any timestep."""
+        return sorted({f.name for fields in self._fields.values() for f in fields})
+
     def get_schema_at_timestep(self, schema, timestep):
         names = self.get_field_names_at_timestep(timestep)
         return schema.create_schema_view([schema.fields[n] for n in schema.fields if n in names])

@@ -4,10 +4,10 @@
 With a petastorm_b200 reader the rows are already device tensors, so the loaders differ from upstream in *where* data
 lives, not in what they yield:
 
-* :class:`DataLoader` keeps the row-at-a-time contract (``collate_fn`` over a list of row dicts, optional
-  ``RandomShufflingBuffer``); ``torch.stack`` then runs on the device.
-* :class:`BatchedDataLoader` is the fast path: whole decoded row-groups go into a device-resident batched shuffling
-  buffer (row gather kernel) and come out as ``{field: tensor[batch_size, ...]}``.
+* :class:`DataLoader` and :class:`BatchedDataLoader` consume whole decoded row-groups: a device-resident batched
+  shuffling buffer (``torch.randperm`` + the row-gather kernel) hands out ``{field: tensor[batch_size, ...]}``; NGram
+  windows are gathered by ``pst_ngram_gather`` into ``[W, L, ...]`` tensors.  ``DataLoader`` falls back to the
+  reference's row loop (``collate_fn`` over a list of row dicts) for a custom ``collate_fn`` or host-valued fields.
 * :class:`InMemBatchedDataLoader` decodes once into HBM and reshuffles per epoch with ``torch.Generator(seed+epoch)``.
 """
 import collections.abc
@@ -113,8 +113,89 @@ class LoaderBase(object):
         self.reader.join()
 
 
+def _is_tensor_column(value):
+    from petastorm_b200.gpu_workers import ScalarColumn
+    return isinstance(value, (torch.Tensor, ScalarColumn))
+
+
+def _as_tensor(value):
+    from petastorm_b200.gpu_workers import ScalarColumn
+    return value.tensor if isinstance(value, ScalarColumn) else value
+
+
+class _DeviceGroups(object):
+    """Whole decoded row-groups of a petastorm_b200 reader as ``{field: tensor[n, ...]}`` (plain rows / batch reader) or
+    :class:`~petastorm_b200.gpu_workers.NGramColumns` (``[W, L, ...]`` per field) - what the device-batched paths of
+    :class:`DataLoader` and :class:`BatchedDataLoader` consume instead of per-row namedtuples.
+
+    ``available()`` peeks at the first row-group: the device path needs a petastorm_b200 reader and tensor-valued
+    columns only (strings, Decimals, nulls and ragged arrays keep the row-at-a-time path of the reference)."""
+
+    def __init__(self, reader):
+        self.reader = reader
+        self._qr = getattr(reader, '_results_queue_reader', None)
+        self._pool = getattr(reader, '_workers_pool', None)
+
+    def available(self):
+        from petastorm_b200.gpu_workers import GpuNGramWindows
+        if self._qr is None or not hasattr(self._qr, 'peek_rowgroup') or getattr(self._qr, '_output', 'torch') != 'torch':
+            return False
+        first = self._qr.peek_rowgroup(self._pool)
+        if first is None:
+            return True            # no data at all: either path yields nothing
+        if isinstance(first, GpuNGramWindows):
+            names = set(first.ngram.get_field_names_at_all_timesteps_names())
+            return all(_is_tensor_column(v) for k, v in first.rows.columns.items() if k in names)
+        return all(_is_tensor_column(v) for v in first.values())
+
+    def __iter__(self):
+        from petastorm_b200.gpu_workers import GpuNGramWindows
+        while True:
+            try:
+                cols = self._qr.read_next_rowgroup(self._pool, raw=True)
+            except StopIteration:
+                self.reader.last_row_consumed = True
+                return
+            if isinstance(cols, GpuNGramWindows):
+                self._raise_for_host_values(dict(cols.rows.columns))
+            if not all(_is_tensor_column(v) for v in cols.values()):
+                self._raise_for_host_values(cols)
+            yield cols
+
+    @staticmethod
+    def _raise_for_host_values(cols):
+        """A later row-group brought values without a tensor form (a null, a ragged array): report it the way the
+        row path would (``_sanitize_pytorch_types`` raises for None and string/object arrays)."""
+        n = min(len(v) for v in cols.values()) if cols else 0
+        for i in range(n):
+            row = {}
+            for k, v in cols.items():
+                item = v[i]
+                row[k] = item.cpu().numpy() if isinstance(item, torch.Tensor) else item
+            _sanitize_pytorch_types(row)
+        raise TypeError('Pytorch does not support the values of this row-group (ragged or non-numeric arrays): '
+                        'fields {}'.format([k for k, v in cols.items() if not _is_tensor_column(v)]))
+
+
+def _nest_ngram_batch(keys, values, timesteps):
+    """``[W, L, ...]`` field tensors of a batch -> ``{offset: {field: tensor[W, ...]}}`` (views, no copies)."""
+    by_name = dict(zip(keys, values))
+    base = min(timesteps)
+    return {t: {name: by_name[name][:, t - base] for name in names if name in by_name}
+            for t, names in timesteps.items()}
+
+
 class DataLoader(LoaderBase):
-    """Row-at-a-time loader: rows -> (optional RandomShufflingBuffer) -> ``collate_fn(list of row dicts)``."""
+    """``petastorm.pytorch.DataLoader`` (petastorm/pytorch.py:131-256): batches of ``batch_size`` rows, optional
+    shuffling queue, ``collate_fn`` to merge rows, last batch possibly partial.
+
+    Over a petastorm_b200 reader with the default ``collate_fn`` and tensor-valued fields the loader never sees a row:
+    whole decoded row-groups go into a device-resident shuffling buffer (``torch.randperm`` + the row-gather kernel)
+    and batches are sliced / gathered on the device - the result is what ``decimal_friendly_collate`` returns for the
+    same rows (``{field: tensor[batch, ...]}``, promoted dtypes), with every field on the device.  A custom
+    ``collate_fn``, host-valued fields (strings, Decimals) or a foreign reader take the reference's row loop.
+    NGram readers (an extension: upstream's loader has no NGram support) yield ``{offset: {field: tensor[batch, ...]}}``.
+    """
 
     def __init__(self, reader, batch_size=1, collate_fn=decimal_friendly_collate, shuffling_queue_capacity=0):
         super(DataLoader, self).__init__()
@@ -124,8 +205,17 @@ class DataLoader(LoaderBase):
         self._batch_acc = []
         self.shuffling_queue_capacity = shuffling_queue_capacity
         self._in_iter = None
+        self.device_batched = None     # set by the first pass: True when the device path was taken
 
     def _iter_impl(self):
+        groups = _DeviceGroups(self.reader)
+        if self.collate_fn is decimal_friendly_collate and groups.available():
+            self.device_batched = True
+            return _iter_device_batches(groups, self.batch_size, self.shuffling_queue_capacity, None)
+        self.device_batched = False
+        return self._iter_rows()
+
+    def _iter_rows(self):
         keys = None
         if self.shuffling_queue_capacity > 0:
             self._shuffling_buffer = RandomShufflingBuffer(self.shuffling_queue_capacity,
@@ -168,6 +258,40 @@ class DataLoader(LoaderBase):
                 self._batch_acc = []
 
 
+def _iter_device_batches(groups, batch_size, shuffling_queue_capacity, transform_fn):
+    """Row-groups -> batches on the device: sanitise dtypes per column, feed the batched shuffling buffer, emit
+    ``{field: tensor[batch, ...]}`` (nested per offset for NGram windows)."""
+    from petastorm_b200.gpu_workers import NGramColumns
+    if shuffling_queue_capacity > 0:
+        min_after = shuffling_queue_capacity - 1
+        buf = BatchedRandomShufflingBuffer(min_after + batch_size, min_after_retrieve=min_after,
+                                           extra_capacity=100000000, batch_size=batch_size)
+    else:
+        buf = BatchedNoopShufflingBuffer(batch_size=batch_size)
+    keys, timesteps = None, None
+
+    def drain():
+        while buf.can_retrieve():
+            batch = buf.retrieve()
+            if timesteps is not None:
+                yield _nest_ngram_batch(keys, batch, timesteps)
+            else:
+                yield dict(zip(keys, batch))
+
+    for cols in groups:
+        if isinstance(cols, NGramColumns):
+            timesteps = cols.timesteps
+        cols = {k: _as_tensor(v) for k, v in cols.items()}
+        _sanitize_pytorch_types(cols)
+        keys = list(cols.keys())
+        buf.add_many(list(cols.values()))
+        for batch in drain():
+            yield batch
+    buf.finish()
+    for batch in drain():
+        yield batch
+
+
 def _as_batch_tensor(value, transform_fn, batched):
     """Column value of a row / row-group -> tensor with a leading row dimension."""
     if isinstance(value, torch.Tensor):
@@ -176,7 +300,8 @@ def _as_batch_tensor(value, transform_fn, batched):
 
 
 class BatchedDataLoader(LoaderBase):
-    """Batched loader: tensors in, ``{field: tensor[batch, ...]}`` out, shuffling through a batched buffer."""
+    """Batched loader (petastorm/pytorch.py:259-370): tensors in, ``{field: tensor[batch, ...]}`` out, shuffling through a
+    batched buffer.  Over a petastorm_b200 reader whole decoded row-groups feed the device buffer directly."""
 
     def __init__(self, reader, batch_size=1, transform_fn=None, shuffling_queue_capacity=0):
         super(BatchedDataLoader, self).__init__()
@@ -186,25 +311,17 @@ class BatchedDataLoader(LoaderBase):
         self._batch_acc = []
         self.shuffling_queue_capacity = shuffling_queue_capacity
         self._in_iter = None
-
-    def _row_groups(self):
-        """Whole decoded row-groups when the reader can hand them out (petastorm_b200 row reader fast path), else the
-        reader's own items."""
-        qr = getattr(self.reader, '_results_queue_reader', None)
-        take_group = getattr(qr, 'read_next_rowgroup', None)
-        if take_group is None or self.reader.batched_output or self.reader.ngram:
-            for row in self.reader:
-                yield row._asdict(), self.reader.batched_output
-            return
-        while True:
-            try:
-                cols = take_group(self.reader._workers_pool)  # pylint: disable=protected-access
-            except StopIteration:
-                self.reader.last_row_consumed = True
-                return
-            yield cols, True
+        self.device_batched = None
 
     def _iter_impl(self):
+        groups = _DeviceGroups(self.reader)
+        if groups.available():
+            self.device_batched = True
+            return _iter_device_batches(groups, self.batch_size, self.shuffling_queue_capacity, self.transform_fn)
+        self.device_batched = False
+        return self._iter_rows()
+
+    def _iter_rows(self):
         keys = None
         if self.shuffling_queue_capacity > 0:
             min_after = self.shuffling_queue_capacity - 1
@@ -214,11 +331,12 @@ class BatchedDataLoader(LoaderBase):
                                                                   batch_size=self.batch_size)
         else:
             self._shuffling_buffer = BatchedNoopShufflingBuffer(batch_size=self.batch_size)
-        for row_as_dict, batched in self._row_groups():
+        for row in self.reader:
+            row_as_dict = row._asdict()
             keys = row_as_dict.keys()
             _sanitize_pytorch_types(row_as_dict)
             for k, v in row_as_dict.items():
-                row_as_dict[k] = _as_batch_tensor(v, self.transform_fn, batched)
+                row_as_dict[k] = _as_batch_tensor(v, self.transform_fn, self.reader.batched_output)
             self._shuffling_buffer.add_many(row_as_dict.values())
             for batch in self._yield_batches(keys):
                 yield batch

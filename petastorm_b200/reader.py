@@ -46,6 +46,22 @@ def _make_cache(cache_type, cache_location, cache_size_limit, cache_row_size_est
     raise ValueError('Unknown cache_type: {}'.format(cache_type))
 
 
+def _resolve_device(device):
+    """CUDA ordinal the reader works on.  ``None`` means the *caller's* current device (``torch.cuda.set_device`` of a
+    DDP rank): the current device is per host thread, so it has to be read here and not on the pool's issuing thread,
+    where it would always be 0."""
+    import torch
+    if device is None:
+        if not torch.cuda.is_available():
+            from petastorm_b200 import native
+            raise native.NativeLibraryError('petastorm_b200 needs a CUDA device (B200, sm_100a); there is no CPU '
+                                            'fallback')
+        return torch.cuda.current_device()
+    if isinstance(device, torch.device):
+        return device.index if device.index is not None else torch.cuda.current_device()
+    return int(device)
+
+
 def _make_pool(reader_pool_type, workers_count, results_queue_size, device):
     if reader_pool_type in ('thread', 'process'):
         # row-groups in flight: one being consumed, one or two decoding (~3 ms), one copying (~5 ms), one queued behind
@@ -79,6 +95,7 @@ def make_reader(dataset_url,
                 output='torch', device=None):
     """Reader over a *Petastorm* dataset (one with a stored Unischema): yields one namedtuple per row with codecs
     decoded on the device.  See :func:`make_batch_reader` for plain Parquet stores."""
+    device = _resolve_device(device)
     dataset_url_or_urls = normalize_dataset_url_or_urls(dataset_url)
     filesystem, dataset_path = get_filesystem_and_path_or_paths(dataset_url_or_urls, hdfs_driver,
                                                                 storage_options=storage_options, filesystem=filesystem)
@@ -131,6 +148,7 @@ def make_batch_reader(dataset_url_or_urls,
                       output='torch', device=None):
     """Reader over a plain Parquet store (native scalar / list-of-primitive columns): yields one namedtuple of column
     arrays per row-group; re-batching is the loader's job."""
+    device = _resolve_device(device)
     dataset_url_or_urls = normalize_dataset_url_or_urls(dataset_url_or_urls)
     filesystem, dataset_path_or_paths = get_filesystem_and_path_or_paths(
         dataset_url_or_urls, hdfs_driver, storage_options=storage_options, filesystem=filesystem)
@@ -177,6 +195,8 @@ class Reader(object):
         self.is_batched_reader = is_batched_reader
         # fail at construction (not at the first next()) when there is no CUDA device: no CPU fallback exists
         from petastorm_b200 import rowgroup
+        device = _resolve_device(device)
+        self.device = device
         rowgroup.get_context(device)
 
         # 1. open the dataset

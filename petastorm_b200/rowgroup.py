@@ -82,17 +82,15 @@ def open_file(path):
 
 
 def forget_file(path):
-    """Drops one file from the open-file cache (it was rewritten)."""
+    """Drops one file from the open-file cache (it was rewritten).  The mapping itself is released when the last plan
+    or decoded row-group that refers to it is gone (they hold a reference): closing it here would leave them with a
+    dangling ``pst_file``."""
     with _ctx_lock:
-        f = _files.pop(path, None)
-        if f is not None:
-            f.close()
+        _files.pop(path, None)
 
 
 def forget_files():
     with _ctx_lock:
-        for f in _files.values():
-            f.close()
         _files.clear()
 
 
@@ -161,6 +159,13 @@ class DecodedRowGroup(object):
             raise DeviceDecodeError('{} (file {}, row-group {}, page table entry {}, detail {})'.format(
                 _DEVICE_ERRORS.get(st[0], 'device decode error %d' % st[0]), self.plan.file.path,
                 self.plan.row_group, st[1], st[2]))
+        for slot, pc in enumerate(self.plan.cols):
+            # a flat nullable column planned without a validity array (chunk statistics: null_count == 0) must not
+            # contain a single level entry below max_def
+            if pc.max_def > 0 and pc.max_rep == 0 and pc.valid_off < 0 and self.null_counts[slot] != 0:
+                raise DeviceDecodeError('column chunk statistics of leaf {} claim null_count == 0 but its pages hold {} '
+                                        'nulls (file {}, row-group {})'.format(pc.column, self.null_counts[slot],
+                                                                               self.plan.file.path, self.plan.row_group))
 
     def column(self, slot):
         pc = self.plan.cols[slot]

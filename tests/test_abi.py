@@ -13,7 +13,7 @@ def test_library_exports_every_declared_symbol():
     for sym in sorted(declared):
         assert hasattr(native.lib, sym), 'libpst_b200.so does not export {}'.format(sym)
     assert set(native.EXPORTED) == declared
-    assert native.lib.pst_abi_version() == 1
+    assert native.lib.pst_abi_version() == 2
     assert native.lib.pst_has_cuda() == 1
 
 

@@ -489,8 +489,14 @@ def _shard_worker(rank, world, port, url, out_dir):
     dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
     kwargs = sharding.sharded_reader_kwargs(url)
     r, w, owners = sharding.broadcast_row_group_assignment(9)
+    # a rank whose listing differs from rank 0's: every rank raises before the table broadcast (no hang)
+    try:
+        sharding.broadcast_row_group_assignment(9 + rank)
+        mismatch = 'no error'
+    except RuntimeError as e:
+        mismatch = 'raised' if 'same dataset' in str(e) else repr(e)
     with open(os.path.join(out_dir, 'rank%d.txt' % rank), 'w') as f:
-        f.write('%r|%r|%r' % (kwargs, (r, w), owners.tolist()))
+        f.write('%r|%r|%r|%s' % (kwargs, (r, w), owners.tolist(), mismatch))
     dist.destroy_process_group()
 
 
@@ -503,6 +509,7 @@ def test_shard_assignment_broadcast_gloo_world2(tmp_path):
     b = open(str(tmp_path / 'rank1.txt')).read().split('|')
     assert a[0] == "{'cur_shard': 0, 'shard_count': 2}" and b[0] == "{'cur_shard': 1, 'shard_count': 2}"
     assert a[2] == b[2] == repr([i % 2 for i in range(9)])
+    assert a[3] == b[3] == 'raised'
     from petastorm_b200 import sharding
     assert sharding.shard_order(9, 2, 1) == [1, 3, 5, 7]
     assert sorted(sharding.shard_order(9, 2, 0, seed=3)) == [0, 2, 4, 6, 8]
@@ -532,22 +539,80 @@ def test_partition_filters_follow_legacy_pyarrow_semantics(tmp_path):
 
 
 def test_planner_resolves_literal_only_snappy_pages_on_the_host(tmp_path):
-    """Incompressible pages leave snappy::RawCompress as one literal per 64 KiB block: the planner reads the fragment
-    boundaries off the tag bytes, and only compressible multi-fragment pages are left for k_snappy_index."""
+    """Incompressible pages leave snappy::RawCompress as literal elements only (one per 64 KiB block): the stream is
+    framed, not compressed.  The planner records where the literal bytes lie and the staging copy lays them down back to
+    back, so the device receives an ordinary uncompressed page image; only compressible pages are left for the Snappy
+    kernels.  The raw image + the copy tiles, emulated here with numpy, must reproduce the column values."""
     import pyarrow as pa
     import pyarrow.parquet as pq
     from petastorm_b200 import native
     n = 300000
     rng = np.random.default_rng(0)
     path = str(tmp_path / 'x.parquet')
-    pq.write_table(pa.table({'noise': rng.integers(0, 2 ** 63 - 1, n, dtype=np.int64),
-                             'narrow': rng.integers(0, 2 ** 20, n, dtype=np.int64)}),
-                   path, compression='snappy', use_dictionary=False, data_page_size=1 << 20)
+    cols = {'noise': rng.integers(0, 2 ** 63 - 1, n, dtype=np.int64),
+            'narrow': rng.integers(0, 2 ** 20, n, dtype=np.int64)}
+    pq.write_table(pa.table(cols), path, compression='snappy', use_dictionary=False, data_page_size=1 << 20)
     f = native.ParquetFile(path)
-    noise = native.Plan(f, 0, [0]).info
+    plan = native.Plan(f, 0, [0])
+    noise = plan.info
     narrow = native.Plan(f, 0, [1]).info
-    assert noise.num_compressed_pages >= 2 and noise.num_index_pages == 0
+    assert noise.num_unwrapped_pages >= 2 and noise.num_compressed_pages == 0 and noise.num_snappy_fragments == 0
     assert narrow.num_compressed_pages >= 2 and narrow.num_index_pages == narrow.num_compressed_pages
+    assert narrow.num_unwrapped_pages == 0
+    # every page of `noise` is PLAIN without nulls: all values travel through copy tiles, none through the page decoder
+    assert noise.num_decode_pages == 0 and noise.num_copy_tiles >= noise.num_unwrapped_pages
+    assert plan.cols[0].valid_off == -1          # chunk statistics: null_count == 0 -> no validity array
+    raw = np.zeros(noise.arena_bytes, dtype=np.uint8)
+    plan.fill_raw(raw.ctypes.data)
+    out = np.zeros(noise.out_bytes, dtype=np.uint8)
+    for i in range(noise.num_copy_tiles):
+        t = plan.copy_tile(i)
+        assert t.src_off % 16 == 0 and t.nbytes <= 65536 and t.valid_off == -1
+        out[t.dst_off:t.dst_off + t.nbytes] = raw[t.src_off:t.src_off + t.nbytes]
+    pc = plan.cols[0]
+    np.testing.assert_array_equal(out[pc.values_off:pc.values_off + 8 * n].view(np.int64), cols['noise'])
+
+
+def test_planner_copy_tiles_v2_pages_and_validity_arrays(tmp_path):
+    """DATA_PAGE_V2 (levels stored uncompressed in front of the values), columns without statistics (validity array
+    kept: the tiles carry the validity bytes to set) and a column with real nulls (general page decoder)."""
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    from petastorm_b200 import native
+    n = 70000
+    rng = np.random.default_rng(1)
+    vals = rng.standard_normal(n).astype(np.float32)
+    holes = vals.astype(object)
+    holes[::7] = None
+    table = pa.table({'x': vals, 'h': pa.array(list(holes), type=pa.float32())})
+    for version, stats, codec in (('2.0', True, 'snappy'), ('1.0', False, 'none'), ('2.0', False, 'snappy')):
+        path = str(tmp_path / 'v{}_{}_{}.parquet'.format(version[0], int(stats), codec))
+        pq.write_table(table, path, compression=codec, use_dictionary=False, data_page_version=version,
+                       write_statistics=stats, data_page_size=64 << 10)
+        f = native.ParquetFile(path)
+        plan = native.Plan(f, 0, [0, 1])
+        info = plan.info
+        x, h = plan.cols
+        assert (x.valid_off == -1) == stats and h.valid_off >= 0
+        raw = np.zeros(info.arena_bytes, dtype=np.uint8)
+        plan.fill_raw(raw.ctypes.data)
+        out = np.zeros(info.out_bytes, dtype=np.uint8)
+        pages = [plan.page(i) for i in range(info.num_pages)]
+        assert all(pg.flags & 2 for pg in pages if pg.column_slot == 0)          # x: all through copy tiles
+        assert not any(pg.flags & 2 for pg in pages if pg.column_slot == 1)      # h has nulls: page decoder
+        assert all(pg.codec == 0 for pg in pages if pg.column_slot == 0)         # random floats: literal-only or stored
+        covered = 0
+        for i in range(info.num_copy_tiles):
+            t = plan.copy_tile(i)
+            out[t.dst_off:t.dst_off + t.nbytes] = raw[t.src_off:t.src_off + t.nbytes]
+            covered += t.nbytes
+            if not stats:
+                assert t.valid_off >= 0 and t.nvalid * 4 == t.nbytes
+                out[t.valid_off:t.valid_off + t.nvalid] = 1
+        assert covered == 4 * n
+        np.testing.assert_array_equal(out[x.values_off:x.values_off + 4 * n].view(np.float32), vals)
+        if not stats:
+            assert out[x.valid_off:x.valid_off + n].all()
 
 
 def _index_fixture_pieces():
