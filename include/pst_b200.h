@@ -103,6 +103,9 @@ typedef struct pst_plan_info {
     int32_t num_copy_tiles;       /* <= 64 KiB work items of k_copy_tiles (PLAIN fixed-width pages without nulls) */
     int32_t num_decode_pages;     /* data pages that go through the general page decoder k_decode_pages */
     int32_t num_snappy_fragments; /* work items of k_snappy_pages */
+    int32_t num_host_indexed_pages; /* multi-fragment Snappy pages of literal-dominated streams (blob columns): the planner
+                                       walks their few tags itself, the others go through k_snappy_index */
+    int32_t reserved_;
 } pst_plan_info;
 int pst_plan_get_info(const pst_plan *p, pst_plan_info *out);
 
@@ -157,6 +160,9 @@ int pst_plan_fill_raw(const pst_plan *p, uint8_t *dst, int64_t first_page, int64
  * ------------------------------------------------------------------------------------------------------------------ */
 int pst_ctx_create(int device, int64_t pinned_cache_bytes, int copy_threads, pst_ctx **out);
 void pst_ctx_destroy(pst_ctx *c);
+/* Changes the budget of the pinned row-group cache of a live context; shrinking below the bytes in use drops every cached
+ * row-group (after a device synchronisation: copies in flight may still read them). */
+int pst_ctx_set_pinned_cache_bytes(pst_ctx *c, int64_t nbytes);
 /* JSON counters: bytes staged, bytes H2D, pages decoded, cache hits… (Reader.diagnostics, petastorm/reader.py:701-703) */
 int pst_ctx_stats_json(pst_ctx *c, char *buf, size_t cap);
 

@@ -130,6 +130,46 @@ def main():
         view = flat_schema.create_schema_view([flat_schema.fields[n] for n in ('key', 'f00', 'i00', 'nullable_int', 'name')])
         res = refshim.reference_batches(url, view, predicate=in_lambda(['key'], lambda key: key % 3 == 0))
         out['flat_predicate_mod3'] = [datasets.digest_row(r) for r in res]
+        # TransformSpec on the batch reader (arrow_reader_worker.py:247-277): func over the pandas DataFrame of a
+        # row-group, edited / added fields (one of them 2-D), removed_fields or selected_fields
+        tview = flat_schema.create_schema_view([flat_schema.fields[n] for n in datasets.FLAT_TRANSFORM_FIELDS])
+        spec = TransformSpec(datasets.flat_transform, edit_fields=datasets.FLAT_TRANSFORM_EDITS,
+                             removed_fields=['i01', 'name'])
+        out['flat_transform_removed'] = [datasets.digest_row(r) for r in refshim.reference_batches(url, tview, transform_spec=spec)]
+        spec = TransformSpec(datasets.flat_transform_select, edit_fields=datasets.FLAT_TRANSFORM_EDITS,
+                             selected_fields=['sum01', 'mat', 'key'])
+        out['flat_transform_selected'] = [datasets.digest_row(r) for r in refshim.reference_batches(url, tview, transform_spec=spec)]
+        spec = TransformSpec(datasets.flat_transform_drop, edit_fields=datasets.FLAT_TRANSFORM_EDITS[:2],
+                             removed_fields=['i01', 'name'])
+        res = refshim.reference_batches(url, tview, transform_spec=spec,
+                                        predicate=in_lambda(['key'], lambda key: key % 3 == 0))
+        out['flat_transform_predicate'] = [datasets.digest_row(r) for r in res]
+        spec = TransformSpec(removed_fields=['i01', 'name'])          # no func: only drops columns
+        out['flat_transform_only_removed'] = [datasets.digest_row(r) for r in refshim.reference_batches(url, tview, transform_spec=spec)]
+
+        # ---- config-shape scenarios (C3/C4/C5 were tested at toy sizes only) ---------------------------
+        # C4: float16 (32,128,128) = 1 MiB values, 64 rows in 4 row-groups, in_set on the key + normalise
+        url = datasets.build('tensor_c4', os.path.join(tmp, 'tensor_c4'), 64, row_group_rows=16)
+        schema = refshim.load_reference_unischema(os.path.join(tmp, 'tensor_c4'))
+        res = refshim.reference_rows(url, schema, predicate=in_set(set(range(0, 64, 2)), 'key'),
+                                     transform_spec=TransformSpec(norm))
+        out['tensor_c4_even_normalized'] = [datasets.digest_row(r) for r in res]
+        out['tensor_c4_rows'] = [datasets.digest_row(r) for r in refshim.reference_rows(url, schema)]
+        # C3: 256 jpeg images in 4 row-groups, row-group order under a seed (labels; pixels are compared within the
+        # nvJPEG tolerance against the oracle's cv2 decode, not through a golden)
+        url = datasets.build('imagenet', os.path.join(tmp, 'imagenet'), 256, row_group_rows=64)
+        schema = refshim.load_reference_unischema(os.path.join(tmp, 'imagenet'))
+        out['imagenet_labels_shuffle_row_groups_seed5'] = [int(r.label) for r in refshim.reference_rows(
+            url, schema, shuffle_row_groups=True, seed=5)]
+        # C5: 120k rows in 2 row-groups with a gap every 37 rows, NGram length 16 over all 13 fields
+        url = datasets.build('series', os.path.join(tmp, 'series_big'), 120000, row_group_rows=60000)
+        schema = refshim.load_reference_unischema(os.path.join(tmp, 'series_big'))
+        names = list(schema.fields.keys())
+        ng = NGram({k: list(schema.fields.values()) for k in range(16)}, delta_threshold=1, timestamp_field=schema.ts)
+        res = refshim.reference_rows(url, schema, ngram=ng)
+        out['series_big_ngram16'] = datasets.ngram_column_digests(res, range(16), names)
+        out['series_big_ngram16_first'] = [{str(k): datasets.digest_row(v) for k, v in sorted(item.items())}
+                                           for item in res[:5]]
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     with open(os.path.join(golden, 'synthetic_expected.json'), 'w') as f:

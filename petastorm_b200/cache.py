@@ -1,6 +1,7 @@
-"""Cache protocol of the readers (petastorm/cache.py:21-39).  The GPU path reads local files through the page cache
-and a pinned row-group cache inside libpst_b200.so, so only the null cache is provided; custom ``CacheBase``
-implementations are honoured by the workers."""
+"""Cache protocol of the readers (petastorm/cache.py:21-39): ``get(key, fill_cache_func)`` of decoded row-groups.
+:class:`NullCache` is the default (the GPU path already keeps raw row-groups in the page cache, a pinned host cache and -
+optionally - an HBM-resident cache, see :mod:`petastorm_b200.rowgroup`); :class:`petastorm_b200.local_disk_cache.
+LocalDiskCache` is ``cache_type='local-disk'``; custom ``CacheBase`` implementations are honoured by the workers."""
 import abc
 
 

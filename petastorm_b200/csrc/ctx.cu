@@ -287,6 +287,23 @@ void pst_ctx_destroy(pst_ctx *c) {
     delete c;
 }
 
+int pst_ctx_set_pinned_cache_bytes(pst_ctx *c, int64_t nbytes) {
+    PST_TRY
+    std::lock_guard<std::mutex> g(c->mu);
+    ck(cudaSetDevice(c->device), "cudaSetDevice");
+    if (nbytes < c->cache_bytes) {
+        // shrinking: in-flight H2D copies may still read the cached buffers
+        ck(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+        for (auto &kv : c->cache)
+            if (kv.second.ptr) cudaFreeHost(kv.second.ptr);
+        c->cache.clear();
+        c->cache_bytes = 0;
+    }
+    c->cache_budget = nbytes;
+    return 0;
+    PST_CATCH(1)
+}
+
 int pst_ctx_stats_json(pst_ctx *c, char *buf, size_t cap) {
     int n = snprintf(buf, cap,
                      "{\"bytes_staged\":%lld,\"bytes_h2d\":%lld,\"pinned_cache_bytes\":%lld,\"pinned_cache_hits\":%lld,"

@@ -332,6 +332,65 @@ static bool literal_segments(const uint8_t *s, int64_t n, int64_t ulen, std::vec
     return op == ulen;
 }
 
+// Fragment positions of a literal-dominated stream, found on the host.  Blob columns (images, tensors, .npy payloads) are
+// practically incompressible: their pages are a handful of long literals with a rare back-reference, and pyarrow puts a
+// whole column chunk of large values into ONE page (the page size is only checked per write batch) - a 134 MB page of
+// 1 MiB tensors has ~2,500 elements.  Walking those tags here costs microseconds, while the device-side index kernel
+// would walk the page as one serial chain.  The walk gives up after `max_elements` elements (a compressible stream: the
+// device indexes it) or when an element straddles a 64 KiB output boundary (k_snappy_index flags such pages for the
+// serial fallback).  pos[0..nfrag] receives the compressed offsets (same convention as k_snappy_index).
+static bool host_fragment_index(const uint8_t *s, int64_t n, int64_t ulen, int nfrag, uint32_t *pos, int64_t max_elements) {
+    int64_t ip = 0;
+    uint64_t v = 0;
+    for (int shift = 0;; shift += 7) {
+        if (ip >= n || shift > 35) return false;
+        const uint8_t b = s[ip++];
+        v |= (uint64_t)(b & 0x7f) << shift;
+        if (!(b & 0x80)) break;
+    }
+    if ((int64_t)v != ulen) return false;
+    int64_t op = 0, next_b = kSnappyFragment, elements = 0;
+    int k = 1;
+    pos[0] = 0;
+    while (ip < n) {
+        if (++elements > max_elements) return false;
+        if (op == next_b) {
+            if (k >= nfrag) return false;
+            pos[k++] = (uint32_t)ip;
+            next_b += kSnappyFragment;
+        }
+        const uint8_t tag = s[ip];
+        int64_t used, made;
+        switch (tag & 3) {
+            case 0: {
+                const int t6 = tag >> 2;
+                if (t6 < 60) {
+                    made = t6 + 1;
+                    used = 1 + made;
+                } else {
+                    const int nb = t6 - 59;
+                    if (ip + 1 + nb > n) return false;
+                    made = 0;
+                    for (int i = 0; i < nb; i++) made |= (int64_t)s[ip + 1 + i] << (8 * i);
+                    made += 1;
+                    used = 1 + nb + made;
+                }
+                break;
+            }
+            case 1: used = 2; made = ((tag >> 2) & 7) + 4; break;
+            case 2: used = 3; made = (tag >> 2) + 1; break;
+            default: used = 5; made = (tag >> 2) + 1; break;
+        }
+        if (made > next_b - op) return false;      // straddles a fragment boundary
+        ip += used;
+        op += made;
+        if (ip > n || op > ulen) return false;
+    }
+    if (ip != n || op != ulen || k != nfrag) return false;
+    pos[nfrag] = (uint32_t)n;
+    return true;
+}
+
 int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_plan **out) {
     PST_TRY
     *out = nullptr;
@@ -498,7 +557,15 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
                     if (d.nfrag > 1) {
                         d.multi_slot = (int32_t)p->multi_pages.size();
                         p->multi_pages.push_back((int32_t)p->pages.size());
-                        p->index_pages.push_back((int32_t)p->pages.size());
+                        // literal-dominated streams (>= 256 stored bytes per element on average) are indexed right
+                        // here; everything else by k_snappy_index
+                        const int64_t lv = (int64_t)d.uncomp_size - values_uncomp;   // V2: uncompressed level bytes
+                        if (host_fragment_index(f->map + payload + lv, (int64_t)d.comp_size - lv, values_uncomp, d.nfrag,
+                                                p->frag_pos_host.data() + d.frag_first,
+                                                std::max<int64_t>(64, ((int64_t)d.comp_size - lv) / 256)))
+                            p->host_indexed_pages++;
+                        else
+                            p->index_pages.push_back((int32_t)p->pages.size());
                     }
                     for (int32_t k = 0; k < d.nfrag; k++)
                         p->snappy_frags.push_back(SnFrag{(int32_t)p->pages.size(), k});
@@ -688,6 +755,7 @@ int pst_plan_get_info(const pst_plan *p, pst_plan_info *out) {
     out->num_compressed_pages = (int32_t)(p->compressed_pages.size() + p->gzip_pages.size());
     out->num_index_pages = (int32_t)p->index_pages.size();
     out->num_unwrapped_pages = (int32_t)p->unwrapped_pages;
+    out->num_host_indexed_pages = (int32_t)p->host_indexed_pages;
     out->num_copy_tiles = (int32_t)p->copy_tiles.size();
     out->num_decode_pages = (int32_t)p->data_pages.size();
     out->num_snappy_fragments = (int32_t)p->snappy_frags.size();

@@ -42,6 +42,7 @@ struct pst_plan {
     std::vector<int32_t> index_pages;        // multi-fragment pages whose fragment positions the device has to find
     std::vector<pst::CopyTile> copy_tiles;   // work items of k_copy_tiles (PF_COPY pages, <= 64 KiB each)
     int64_t unwrapped_pages = 0;             // literal-only Snappy pages delivered as uncompressed images
+    int64_t host_indexed_pages = 0;          // multi-fragment Snappy pages whose fragment positions the planner found
     int64_t copy_tiles_off = 0;
     std::vector<uint32_t> frag_pos_host;     // fragment-position table as far as the host knows it (literal-only pages)
     int64_t frag_pos_count = 0;              // entries of the fragment-position table (sum of nfrag + 1)

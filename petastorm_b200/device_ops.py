@@ -14,7 +14,12 @@ _NORM_DTYPE = {torch.uint8: 0, torch.float16: 1, torch.float32: 2, torch.int32: 
                torch.float64: 6}
 
 
+#: C-ABI kernel-launching calls made through this module (bench.py's gpu_launches); a counter, not a lock-step log
+LAUNCH_CALLS = [0]
+
+
 def _stream():
+    LAUNCH_CALLS[0] += 1
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -78,6 +78,25 @@ def encode_row(schema, row):
     return out
 
 
+def arrow_schema_of(schema, partition_by=None):
+    """The pyarrow schema a dataset with this Unischema is stored with (codec fields are binary blobs)."""
+    import pyarrow as pa
+    names = [n for n in schema.fields.keys() if n != partition_by]
+    return pa.schema([pa.field(n, _arrow_type_of(schema.fields[n]), nullable=bool(schema.fields[n].nullable))
+                      for n in names])
+
+
+def write_common_metadata(output_dir, schema, row_groups_per_file, partition_by=None):
+    """``_common_metadata`` of a Petastorm dataset: the pickled Unischema and the row-group count of every file
+    (``{path relative to output_dir: num_row_groups}``) - what ``materialize_dataset`` adds after the Spark job
+    (petastorm/etl/dataset_metadata.py:194-241).  Lets part files be written independently (e.g. in parallel)."""
+    import pyarrow.parquet as pq
+    meta = {UNISCHEMA_KEY: pickle_unischema_reference_compatible(schema),
+            ROW_GROUPS_PER_FILE_KEY: json.dumps(row_groups_per_file).encode()}
+    pq.write_metadata(arrow_schema_of(schema, partition_by).with_metadata(meta),
+                      os.path.join(output_dir, '_common_metadata'))
+
+
 def write_petastorm_dataset(output_dir, schema, rows, rows_per_file=None, row_group_rows=None, compression='snappy',
                             partition_by=None, data_page_size=None, use_dictionary=True):
     """Encode `rows` (iterable of dicts) and write them as a Petastorm dataset under `output_dir`.
@@ -91,8 +110,7 @@ def write_petastorm_dataset(output_dir, schema, rows, rows_per_file=None, row_gr
     import pyarrow.parquet as pq
     os.makedirs(output_dir, exist_ok=True)
     names = [n for n in schema.fields.keys() if n != partition_by]
-    arrow_schema = pa.schema([pa.field(n, _arrow_type_of(schema.fields[n]), nullable=bool(schema.fields[n].nullable))
-                              for n in names])
+    arrow_schema = arrow_schema_of(schema, partition_by)
     buckets = {}
     for row in rows:
         enc = encode_row(schema, row)
@@ -116,9 +134,7 @@ def write_petastorm_dataset(output_dir, schema, rows, rows_per_file=None, row_gr
                            use_dictionary=use_dictionary, **kwargs)
             per_file[os.path.relpath(path, output_dir)] = pq.ParquetFile(path).metadata.num_row_groups
             written.append(path)
-    meta = {UNISCHEMA_KEY: pickle_unischema_reference_compatible(schema),
-            ROW_GROUPS_PER_FILE_KEY: json.dumps(per_file).encode()}
-    pq.write_metadata(arrow_schema.with_metadata(meta), os.path.join(output_dir, '_common_metadata'))
+    write_common_metadata(output_dir, schema, per_file, partition_by)
     return written
 
 

@@ -119,11 +119,9 @@ class _GpuWorkerBase(WorkerBase):
             self._decoder = rowgroup.RowGroupDecoder(self._options.device)
         return self._decoder
 
-    def _read_raw(self, piece, field_names):
-        """plan + H2D + device decode of the leaf columns behind `field_names` (partition columns excluded)."""
-        import time
-        t0 = time.perf_counter()
-        dec = self._get_decoder()
+    def _field_slots(self, piece, field_names):
+        """(open file, {field name: plan slot}, [leaf column ids]) of the leaf columns behind `field_names`
+        (partition columns are served from the piece's keys, not from the file)."""
         pfile = rowgroup.open_file(piece.path)
         partition_names = self._options.partitions.partition_names if self._options.partitions else set()
         leaves = pfile.schema['leaves']
@@ -143,6 +141,14 @@ class _GpuWorkerBase(WorkerBase):
                 raise ValueError('Field {} maps to a nested parquet structure that is not supported'.format(name))
             name_to_slot[name] = len(leaf_ids)
             leaf_ids.append(ids[0])
+        return pfile, name_to_slot, leaf_ids
+
+    def _read_raw(self, piece, field_names):
+        """plan + H2D + device decode of the leaf columns behind `field_names` (partition columns excluded)."""
+        import time
+        t0 = time.perf_counter()
+        dec = self._get_decoder()
+        pfile, name_to_slot, leaf_ids = self._field_slots(piece, field_names)
         num_rows = pfile.row_group_num_rows(piece.row_group)
         decoded = None
         if leaf_ids:
@@ -223,6 +229,7 @@ class _GpuWorkerBase(WorkerBase):
         if self._decoder is not None:
             d['gpu_launches'] = self._decoder.launches
             d['h2d_bytes'] = self._decoder.h2d_bytes
+            d['hbm_cache_hits'] = self._decoder.hbm_cache_hits
             d.update(self._decoder.ctx.stats())
         return d
 
@@ -1188,6 +1195,51 @@ class GpuPyDictWorker(_GpuWorkerBase):
         if starts_dev is None:
             starts = self._ngram.window_starts_host(ts_list if ts_list is not None else list(ts.cpu().numpy()))
         return GpuNGramWindows(rows, starts, self._ngram, starts_dev)
+
+
+# ---- host images of decoded row-groups (LocalDiskCache) -------------------------------------------------------------------
+def _host_value(v):
+    if isinstance(v, ScalarColumn):
+        return ('scalar', v._values(), v.np_type)  # pylint: disable=protected-access
+    if isinstance(v, torch.Tensor):
+        return ('tensor', v.cpu().numpy())
+    if isinstance(v, list) and any(isinstance(x, torch.Tensor) for x in v):
+        return ('list', [x.cpu().numpy() if isinstance(x, torch.Tensor) else x for x in v], True)
+    return ('host', v)
+
+
+def _device_value(item, device):
+    kind = item[0]
+    if kind == 'scalar':
+        return ScalarColumn(torch.from_numpy(item[1]).to(device), item[2], item[1])
+    if kind == 'tensor':
+        return torch.from_numpy(item[1]).to(device)
+    if kind == 'list':
+        return [torch.from_numpy(x).to(device) if isinstance(x, np.ndarray) and x.dtype in _TORCH_OF_NUMPY else x
+                for x in item[1]]
+    return item[1]
+
+
+def to_host_payload(value):
+    """Picklable host image of a decoded row-group (:class:`GpuBatch` / :class:`GpuRowGroupRows`; None stays None)."""
+    if value is None:
+        return None
+    if isinstance(value, PendingRowGroup):
+        value = value.resolve()
+    value.wait()
+    torch.cuda.current_stream().synchronize()
+    kind = 'batch' if isinstance(value, GpuBatch) else 'rows'
+    return {'kind': kind, 'num_rows': value.num_rows, 'columns': {k: _host_value(v) for k, v in value.columns.items()}}
+
+
+def from_host_payload(payload, device=None):
+    """Inverse of :func:`to_host_payload`: the columns go back to the (current) device with one H2D copy each."""
+    if payload is None:
+        return None
+    device = torch.device('cuda', torch.cuda.current_device()) if device is None else device
+    cols = {k: _device_value(v, device) for k, v in payload['columns'].items()}
+    cls = GpuBatch if payload['kind'] == 'batch' else GpuRowGroupRows
+    return cls(cols, payload['num_rows'], [])
 
 
 def _npy_header_len(prefix):

@@ -44,7 +44,7 @@ class PlanInfo(Structure):
                 ('payload_bytes', c_int64), ('uncompressed_bytes', c_int64), ('num_pages', c_int32),
                 ('num_columns', c_int32), ('num_compressed_pages', c_int32), ('num_index_pages', c_int32),
                 ('num_unwrapped_pages', c_int32), ('num_copy_tiles', c_int32), ('num_decode_pages', c_int32),
-                ('num_snappy_fragments', c_int32)]
+                ('num_snappy_fragments', c_int32), ('num_host_indexed_pages', c_int32), ('reserved_', c_int32)]
 
 
 class PlanColumn(Structure):
@@ -96,6 +96,7 @@ _sig('pst_plan_get_copy_tile', c_int, c_void_p, c_int, POINTER(CopyTile))
 _sig('pst_ctx_create', c_int, c_int, c_int64, c_int, POINTER(c_void_p))
 _sig('pst_ctx_destroy', None, c_void_p)
 _sig('pst_ctx_stats_json', c_int, c_void_p, c_char_p, c_size_t)
+_sig('pst_ctx_set_pinned_cache_bytes', c_int, c_void_p, c_int64)
 _sig('pst_plan_upload', c_int, c_void_p, c_void_p, c_uint64, c_uint64)
 _sig('pst_plan_decode', c_int, c_void_p, c_void_p, c_uint64, c_uint64, c_uint64, c_uint64, POINTER(c_int))
 _sig('pst_plan_decode_timed', c_int, c_void_p, c_void_p, c_uint64, c_uint64, c_uint64, c_uint64, POINTER(c_float))
@@ -129,7 +130,7 @@ EXPORTED = [
     'pst_file_schema_json', 'pst_file_kv_metadata', 'pst_file_num_kv', 'pst_file_kv_at', 'pst_file_chunk_info',
     'pst_plan_create', 'pst_plan_destroy', 'pst_plan_get_info', 'pst_plan_get_column', 'pst_plan_fill_raw',
     'pst_plan_get_page', 'pst_plan_get_copy_tile',
-    'pst_ctx_create', 'pst_ctx_destroy', 'pst_ctx_stats_json', 'pst_plan_upload', 'pst_plan_decode', 'pst_plan_decode_timed',
+    'pst_ctx_create', 'pst_ctx_destroy', 'pst_ctx_stats_json', 'pst_ctx_set_pinned_cache_bytes', 'pst_plan_upload', 'pst_plan_decode', 'pst_plan_decode_timed',
     'pst_nullable_to_f64', 'pst_narrow_int32', 'pst_gather_rows', 'pst_npy_batch', 'pst_blob_prefix', 'pst_zip_inflate_batch', 'pst_png_work_bytes',
     'pst_png_batch', 'pst_jpeg_available', 'pst_jpeg_backend', 'pst_jpeg_batch', 'pst_mask_in_set_i64',
     'pst_mask_md5_split_i64', 'pst_compact_tmp_bytes', 'pst_mask_compact', 'pst_normalize',
@@ -255,6 +256,9 @@ class Context(object):
     @property
     def handle(self):
         return self._h
+
+    def set_pinned_cache_bytes(self, nbytes):
+        check(lib.pst_ctx_set_pinned_cache_bytes(self._h, int(nbytes)), 'pst_ctx_set_pinned_cache_bytes')
 
     def stats(self):
         buf = ctypes.create_string_buffer(1024)

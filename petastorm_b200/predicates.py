@@ -50,6 +50,16 @@ class in_set(PredicateBase):
         self._inclusion_values = set(inclusion_values)
         self._predicate_field = predicate_field
         self._device_set = None
+        self._sorted_ints = None
+
+    def __getstate__(self):
+        # pickle-compatible with the reference class (two attributes); the device caches are rebuilt on demand
+        return {'_inclusion_values': self._inclusion_values, '_predicate_field': self._predicate_field}
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._device_set = None
+        self._sorted_ints = None
 
     def get_fields(self):
         return {self._predicate_field}
@@ -63,16 +73,19 @@ class in_set(PredicateBase):
         col = columns.get(self._predicate_field)
         if col is None or not _is_int_tensor(col):
             return None
-        try:
-            ints = sorted(int(v) for v in self._inclusion_values
-                          if isinstance(v, (int, np.integer)) and not isinstance(v, (bool, np.bool_)))
-        except (TypeError, ValueError):
+        if self._sorted_ints is None:      # once per predicate: the set may hold millions of keys
+            try:
+                ints = sorted(int(v) for v in self._inclusion_values
+                              if isinstance(v, (int, np.integer)) and not isinstance(v, (bool, np.bool_)))
+            except (TypeError, ValueError):
+                ints = []
+            # non-integer members: python equality semantics differ, stay on the host form
+            self._sorted_ints = False if len(ints) != len(self._inclusion_values) else \
+                np.asarray([v for v in ints if -2 ** 63 <= v < 2 ** 63], dtype=np.int64)
+        if self._sorted_ints is False:
             return None
-        if len(ints) != len(self._inclusion_values):
-            return None  # non-integer members: python equality semantics differ, stay on the host form
         if self._device_set is None or self._device_set.device != col.device:
-            ints = [v for v in ints if -2 ** 63 <= v < 2 ** 63]
-            self._device_set = torch.tensor(ints, dtype=torch.int64, device=col.device)
+            self._device_set = torch.from_numpy(self._sorted_ints).to(col.device)
         return device_ops.mask_in_set(col.contiguous(), self._device_set)
 
 

@@ -258,9 +258,65 @@ class DataLoader(LoaderBase):
                 self._batch_acc = []
 
 
+class _RowPacker(object):
+    """Packs the narrow columns of a row-group (scalars, short vectors, NGram windows of scalars: <= ``SMALL`` bytes per
+    row) into ONE ``uint8 [n, R]`` tensor, so that the shuffling buffer moves a row with one gather instead of one per
+    field (a C5 window has 13 fields; the buffer is launch-bound otherwise).  A batch is split back into typed views
+    of the packed batch buffer (no copies): narrow fields come out as strided views ``[batch, ...]``.  Wide columns
+    (images, tensors) stay separate tensors."""
+
+    SMALL = 256
+
+    def __init__(self, columns):
+        self.keys = list(columns.keys())
+        self.small, self.big = [], []
+        off = 0
+        for k in self.keys:
+            t = columns[k]
+            item = t.element_size()
+            nb = item * int(np.prod(t.shape[1:], dtype=np.int64))
+            if 0 < nb <= self.SMALL:
+                off = (off + item - 1) // item * item
+                self.small.append((k, off, nb, t.dtype, tuple(t.shape[1:])))
+                off += nb
+            else:
+                self.big.append(k)
+        if len(self.small) < 2:          # nothing to gain: keep every column as it is
+            self.big = self.keys
+            self.small = []
+        self.row_bytes = (off + 15) // 16 * 16
+
+    def pack(self, columns):
+        """list of buffer columns: [packed narrow fields (if any)] + wide columns"""
+        out = []
+        if self.small:
+            n = columns[self.small[0][0]].shape[0]
+            packed = torch.empty((n, self.row_bytes), dtype=torch.uint8, device=columns[self.small[0][0]].device)
+            for k, off, nb, dtype, shape in self.small:
+                t = columns[k]
+                if t.dtype != dtype or tuple(t.shape[1:]) != shape:
+                    raise TypeError('field {} changed from {}{} to {}{} between row-groups'.format(
+                        k, dtype, shape, t.dtype, tuple(t.shape[1:])))
+                packed[:, off:off + nb] = t.contiguous().reshape(n, -1).view(torch.uint8)
+            out.append(packed)
+        out.extend(columns[k] for k in self.big)
+        return out
+
+    def unpack(self, batch):
+        res = {}
+        rest = batch
+        if self.small:
+            packed, rest = batch[0], batch[1:]
+            n = packed.shape[0]
+            for k, off, nb, dtype, shape in self.small:
+                res[k] = packed[:, off:off + nb].view(dtype).reshape((n,) + shape)
+        res.update(zip(self.big, rest))
+        return {k: res[k] for k in self.keys}
+
+
 def _iter_device_batches(groups, batch_size, shuffling_queue_capacity, transform_fn):
-    """Row-groups -> batches on the device: sanitise dtypes per column, feed the batched shuffling buffer, emit
-    ``{field: tensor[batch, ...]}`` (nested per offset for NGram windows)."""
+    """Row-groups -> batches on the device: sanitise dtypes per column, pack the narrow columns, feed the batched
+    shuffling buffer, emit ``{field: tensor[batch, ...]}`` (nested per offset for NGram windows)."""
     from petastorm_b200.gpu_workers import NGramColumns
     if shuffling_queue_capacity > 0:
         min_after = shuffling_queue_capacity - 1
@@ -268,23 +324,24 @@ def _iter_device_batches(groups, batch_size, shuffling_queue_capacity, transform
                                            extra_capacity=100000000, batch_size=batch_size)
     else:
         buf = BatchedNoopShufflingBuffer(batch_size=batch_size)
-    keys, timesteps = None, None
+    packer, timesteps = None, None
 
     def drain():
         while buf.can_retrieve():
-            batch = buf.retrieve()
+            batch = packer.unpack(buf.retrieve())
             if timesteps is not None:
-                yield _nest_ngram_batch(keys, batch, timesteps)
+                yield _nest_ngram_batch(list(batch.keys()), list(batch.values()), timesteps)
             else:
-                yield dict(zip(keys, batch))
+                yield batch
 
     for cols in groups:
         if isinstance(cols, NGramColumns):
             timesteps = cols.timesteps
         cols = {k: _as_tensor(v) for k, v in cols.items()}
         _sanitize_pytorch_types(cols)
-        keys = list(cols.keys())
-        buf.add_many(list(cols.values()))
+        if packer is None:
+            packer = _RowPacker(cols)
+        buf.add_many(packer.pack(cols))
         for batch in drain():
             yield batch
     buf.finish()

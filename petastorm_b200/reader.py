@@ -41,8 +41,8 @@ def _make_cache(cache_type, cache_location, cache_size_limit, cache_row_size_est
     if cache_type is None or cache_type == NULL_CACHE:
         return NullCache()
     if cache_type == LOCAL_DISK_CACHE:
-        raise ValueError('cache_type="local-disk" is not available: the GPU path reads local files through the page '
-                         'cache and a pinned row-group cache (rowgroup.set_pinned_cache_bytes); pass cache_type="null"')
+        from petastorm_b200.local_disk_cache import LocalDiskCache
+        return LocalDiskCache(cache_location, cache_size_limit, cache_row_size_estimate, **(cache_extra_settings or {}))
     raise ValueError('Unknown cache_type: {}'.format(cache_type))
 
 

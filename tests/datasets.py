@@ -42,11 +42,15 @@ def _schemas():
         UnischemaField('key', np.int32, (), ScalarCodec(T.IntegerType()), False),
         UnischemaField('tensor', np.float16, (8, 16, 16), NdarrayCodec(), False),
     ])
+    tensor_c4 = Unischema('TensorC4Schema', [
+        UnischemaField('key', np.int32, (), ScalarCodec(T.IntegerType()), False),
+        UnischemaField('tensor', np.float16, (32, 128, 128), NdarrayCodec(), False),
+    ])
     imagenet = Unischema('ImagenetSchema', [
         UnischemaField('label', np.int32, (), ScalarCodec(T.IntegerType()), False),
         UnischemaField('image', np.uint8, (224, 224, 3), CompressedImageCodec('jpeg', 80), False),
     ])
-    return dict(hello=hello, test=test, series=series, tensor=tensor, imagenet=imagenet)
+    return dict(hello=hello, test=test, series=series, tensor=tensor, tensor_c4=tensor_c4, imagenet=imagenet)
 
 
 def schema(name):
@@ -107,6 +111,14 @@ def tensor_rows(n, seed=8):
         yield {'key': np.int32(i), 'tensor': rng.standard_normal((8, 16, 16)).astype(np.float16)}
 
 
+def tensor_c4_rows(n, seed=18):
+    """C4 at its real shape: one value = 128-byte .npy header + 1 MiB of float16 (larger than a data page, 17 Snappy
+    fragments per value)."""
+    rng = np.random.default_rng(seed)
+    for i in range(n):
+        yield {'key': np.int32(i), 'tensor': rng.standard_normal((32, 128, 128), dtype=np.float32).astype(np.float16)}
+
+
 def imagenet_rows(n, seed=3):
     import cv2
     rng = np.random.default_rng(seed)
@@ -124,7 +136,7 @@ def build(kind, out_dir, n, **kw):
     from petastorm_b200.etl.dataset_writer import write_petastorm_dataset
     s = schema(kind)
     rows = {'hello': hello_rows, 'test': test_rows, 'series': series_rows, 'tensor': tensor_rows,
-            'imagenet': imagenet_rows}[kind](n)
+            'tensor_c4': tensor_c4_rows, 'imagenet': imagenet_rows}[kind](n)
     write_petastorm_dataset(out_dir, s, rows, **kw)
     return 'file://' + out_dir
 
@@ -193,6 +205,53 @@ def digest(value):
     if isinstance(value, (bytes, bytearray)):
         return 'bytes:' + hashlib.sha1(bytes(value)).hexdigest()[:16]
     return '{}:{!r}'.format(type(value).__name__, value)
+
+
+def flat_transform(df):
+    """TransformSpec.func of the batch-reader scenarios: receives the row-group as a pandas DataFrame
+    (petastorm/arrow_reader_worker.py:247-251), edits a column, adds a scalar and a 2-D field."""
+    df['f00'] = df['f00'] * np.float32(2)
+    df['sum01'] = (df['i00'] + df['i01']).astype(np.int64)
+    df['mat'] = df['key'].map(lambda k: np.full((2, 3), k, dtype=np.float32) + np.arange(6, dtype=np.float32).reshape(2, 3))
+    return df
+
+
+def flat_transform_drop(df):
+    """Same, for the predicate path: upstream applies func WITHOUT the removed-fields post-processing there
+    (arrow_reader_worker.py:342-345), so the function itself returns exactly the transformed schema's columns."""
+    df = flat_transform(df.copy())
+    del df['i01']
+    del df['name']
+    del df['mat']     # upstream does not ravel multi-dimensional fields on the predicate path (from_pandas would fail)
+    return df
+
+
+def flat_transform_select(df):
+    """selected_fields narrows the schema, not the data: the function returns exactly the selected columns (a result
+    with other columns is a ValueError upstream, arrow_reader_worker.py:261-268)."""
+    return flat_transform(df.copy())[['sum01', 'mat', 'key']]
+
+
+FLAT_TRANSFORM_FIELDS = ['key', 'f00', 'i00', 'i01', 'name']
+FLAT_TRANSFORM_EDITS = [('f00', np.float32, (), False), ('sum01', np.int64, (), False), ('mat', np.float32, (2, 3), False)]
+
+
+def ngram_column_digests(windows, offsets, names):
+    """{"<offset>.<field>": sha1 over the values of that field at that offset across all windows} + the window count.
+    `windows` is an iterable of {offset: row-like}; used for NGram scenarios too large for per-window digests."""
+    cols = {(o, n): [] for o in offsets for n in names}
+    count = 0
+    for w in windows:
+        count += 1
+        for o in offsets:
+            item = w[o]
+            d = item._asdict() if hasattr(item, '_asdict') else item
+            for n in names:
+                cols[(o, n)].append(d[n])
+    out = {'windows': count}
+    for (o, n), vals in sorted(cols.items()):
+        out['%d.%s' % (o, n)] = digest(np.asarray(vals))
+    return out
 
 
 def digest_row(row):

@@ -65,11 +65,52 @@ def test_dataloader_row_reader(synth, capacity):
     order = [int(r['id']) for r in port.read_rows(url, {'id': oracle_specs(load_schema(url[7:]))['id']})]
     seen = _check_batches(batches, exp, 7, ordered_ids=order if capacity == 0 else None)
     assert [len(b['id']) for b in batches[:-1]] == [7] * (len(batches) - 1)
+    assert loader.device_batched is True     # whole row-groups through the device shuffling buffer, no per-row Python
     import torch
+    assert all(v.is_cuda for v in batches[0].values())
     assert batches[0]['image_png'].is_cuda and batches[0]['matrix_uint16'].dtype == torch.int32
     assert batches[0]['matrix_uint32'].dtype == torch.int64 and batches[0]['id_odd'].dtype == torch.uint8
     if capacity >= 11:
         assert seen != order  # decorrelated (probability of identity is negligible)
+
+
+def test_dataloader_custom_collate_takes_the_row_loop(synth):
+    """A user collate_fn sees exactly what upstream hands it: a list of row dicts (petastorm/pytorch.py:131-248)."""
+    from petastorm_b200 import make_reader
+    from petastorm_b200.pytorch import DataLoader
+    url = synth['test']
+    seen = []
+
+    def collate(rows):
+        assert isinstance(rows, list) and isinstance(rows[0], dict)
+        seen.append(len(rows))
+        return [int(r['id']) for r in rows]
+
+    with DataLoader(make_reader(url, schema_fields=['id', 'matrix'], shuffle_row_groups=False), batch_size=9,
+                    collate_fn=collate) as loader:
+        ids = sum(list(loader), [])
+    assert loader.device_batched is False and ids == list(range(40)) and seen == [9, 9, 9, 9, 4]
+
+
+def test_dataloader_batch_reader_device_path(synth):
+    """DataLoader over make_batch_reader (upstream transposes every row-group into per-row tuples, pytorch.py:207-216):
+    same batches, formed on the device."""
+    import torch
+    from petastorm_b200 import make_batch_reader
+    from petastorm_b200.pytorch import DataLoader
+    url = synth['flat']
+    cols = ['key', 'f00', 'i00', 'small', 'flag']
+    exp = port.read_batches(url, columns=cols)
+    exp = {k: np.concatenate([e[k] for e in exp]) for k in cols}
+    with DataLoader(make_batch_reader(url, schema_fields=cols, shuffle_row_groups=False), batch_size=128) as loader:
+        batches = list(loader)
+    assert loader.device_batched is True
+    assert [len(b['key']) for b in batches] == [128] * 4 + [88]
+    for k in cols:
+        got = torch.cat([b[k] for b in batches]).cpu().numpy()
+        e = exp[k].astype(np.uint8) if exp[k].dtype == np.bool_ else exp[k]
+        np.testing.assert_array_equal(got, e)
+        assert got.dtype == e.dtype
 
 
 def test_dataloader_rejects_strings_and_nulls(synth):

@@ -696,3 +696,83 @@ def test_update_common_metadata_keeps_the_other_keys(tmp_path):
         assert sorted(loaded['by_id'].get_row_group_indexes(4)) == [0, 1]
         assert sorted(loaded['by_id'].get_row_group_indexes(3)) == [0]
     assert list(dm.get_schema(dm.ParquetDataset(path)).fields) == list(dm.get_schema(ds).fields)
+
+
+def test_weighted_sampling_reader_contract():
+    """petastorm/tests/test_weighted_sampling_reader.py: mixing by probability, validation of mismatching readers,
+    stop when the first reader is exhausted."""
+    from collections import namedtuple
+    from petastorm_b200.weighted_sampling_reader import WeightedSamplingReader
+
+    class FakeSchema(object):
+        def __init__(self, names):
+            self.fields = {n: None for n in names}
+
+    class FakeReader(object):
+        def __init__(self, value, n, names=('x',), batched=False, ngram=None):
+            self._value, self._left = value, n
+            self.schema, self.batched_output, self.ngram = FakeSchema(names), batched, ngram
+            self.last_row_consumed = False
+            self.stopped = self.joined = False
+
+        def __iter__(self):
+            return self
+
+        def __next__(self):
+            if self._left == 0:
+                self.last_row_consumed = True
+                raise StopIteration
+            self._left -= 1
+            return self._value
+
+        def stop(self):
+            self.stopped = True
+
+        def join(self):
+            self.joined = True
+
+    np.random.seed(4)
+    a, b = FakeReader('a', 10 ** 6), FakeReader('b', 10 ** 6)
+    with WeightedSamplingReader([a, b], [1, 3]) as mixed:      # not normalised on purpose
+        draws = [next(mixed) for _ in range(4000)]
+    assert a.stopped and a.joined and b.stopped and b.joined
+    assert 0.70 < draws.count('b') / 4000.0 < 0.80
+    short = WeightedSamplingReader([FakeReader('a', 3), FakeReader('b', 10 ** 6)], [0.5, 0.5])
+    assert len(list(short)) >= 3 and short.last_row_consumed
+    with pytest.raises(ValueError, match='Two or more'):
+        WeightedSamplingReader([a], [1.0])
+    with pytest.raises(ValueError, match='same length'):
+        WeightedSamplingReader([a, b], [1.0])
+    with pytest.raises(ValueError, match='batched_output'):
+        WeightedSamplingReader([a, FakeReader('c', 1, batched=True)], [0.5, 0.5])
+    with pytest.raises(ValueError, match='same schema'):
+        WeightedSamplingReader([a, FakeReader('c', 1, names=('y',))], [0.5, 0.5])
+    with pytest.raises(ValueError, match='ngram'):
+        WeightedSamplingReader([a, FakeReader('c', 1, ngram=namedtuple('N', 'a')(1))], [0.5, 0.5])
+
+
+def test_local_disk_cache_validation_and_eviction(tmp_path):
+    """petastorm/local_disk_cache.py:23-82: the shard-capacity sanity check, and least-recently-stored eviction.  The
+    values a reader stores are host images of decoded row-groups; the eviction logic is exercised here through the
+    file layer with a fake payload."""
+    from petastorm_b200 import gpu_workers
+    from petastorm_b200.local_disk_cache import LocalDiskCache
+    with pytest.raises(ValueError, match='size_limit_bytes / shards'):
+        LocalDiskCache(str(tmp_path / 'c0'), 1000, 100, shards=6)
+    LocalDiskCache(str(tmp_path / 'c1'), 1000, 100, shards=6, eviction_policy='none')     # no check without eviction
+    cache = LocalDiskCache(str(tmp_path / 'c2'), 40000, 100, shards=3)
+    real_to, real_from = gpu_workers.to_host_payload, gpu_workers.from_host_payload
+    gpu_workers.to_host_payload = lambda v: v
+    gpu_workers.from_host_payload = lambda p, device=None: p
+    try:
+        calls = []
+        for k in range(8):
+            assert cache.get('key%d' % k, lambda k=k: calls.append(k) or {'blob': b'x' * 9000, 'k': k})['k'] == k
+        assert calls == list(range(8)) and cache.volume() <= 40000 + 9100
+        assert cache.get('key7', lambda: calls.append('again'))['k'] == 7 and calls[-1] == 7      # hit
+        assert cache.get('key0', lambda: calls.append('refill') or {'k': 0})['k'] == 0 and calls[-1] == 'refill'  # evicted
+        assert cache.hits == 1 and cache.misses == 9
+    finally:
+        gpu_workers.to_host_payload, gpu_workers.from_host_payload = real_to, real_from
+    cache.cleanup()
+    assert not os.path.exists(str(tmp_path / 'c2'))

@@ -93,3 +93,37 @@ def test_port_batches_match_reference(synth):
     assert [[int(k) for k in r['key']] for r in got] == exp['flat_keys_shuffled_seed11']
     got = port.read_batches(synth['flat'], columns=cols, shuffle_row_drop_partitions=2)
     assert [[int(k) for k in r['key']] for r in got] == exp['flat_keys_drop_partitions_2']
+
+
+def test_port_batch_transform_matches_reference(synth):
+    """TransformSpec on the batch reader (arrow_reader_worker.py:247-277): func over the DataFrame of a row-group,
+    removed / selected fields."""
+    exp = golden('synthetic_expected.json')
+    cols = datasets.FLAT_TRANSFORM_FIELDS
+    got = port.read_batches(synth['flat'], columns=cols, transform_func=datasets.flat_transform,
+                            removed_fields=['i01', 'name'])
+    assert [datasets.digest_row(r) for r in got] == exp['flat_transform_removed']
+    got = port.read_batches(synth['flat'], columns=cols, transform_func=datasets.flat_transform_select)
+    assert [datasets.digest_row(r) for r in got] == exp['flat_transform_selected']
+    got = port.read_batches(synth['flat'], columns=cols, removed_fields=['i01', 'name'])
+    assert [datasets.digest_row(r) for r in got] == exp['flat_transform_only_removed']
+
+
+def test_port_config_shapes_match_reference(tmp_path):
+    """C4 (1 MiB float16 tensors, predicate + normalise) and C5 (120k rows, NGram 16 over 13 fields) at config shape."""
+    from petastorm_b200.predicates import in_set
+    exp = golden('synthetic_expected.json')
+    url = datasets.build('tensor_c4', str(tmp_path / 'c4'), 64, row_group_rows=16)
+    specs = _specs(url)
+
+    def norm(row):
+        row['tensor'] = ((row['tensor'].astype(np.float32) - np.float32(0.25)) / np.float32(1.5)).astype(np.float16)
+        return row
+
+    res = port.read_rows(url, specs, predicate=in_set(set(range(0, 64, 2)), 'key'), transform_func=norm)
+    assert [datasets.digest_row(r) for r in res] == exp['tensor_c4_even_normalized']
+    url = datasets.build('series', str(tmp_path / 'c5'), 120000, row_group_rows=60000)
+    specs = _specs(url)
+    names = list(specs.keys())
+    res = port.read_rows(url, specs, ngram=dict(fields={k: names for k in range(16)}, ts='ts', delta=1))
+    assert datasets.ngram_column_digests(res, range(16), names) == exp['series_big_ngram16']
