@@ -239,6 +239,14 @@ int pst_jpeg_available(void);  /* 1 when libnvjpeg could be dlopen'ed */
 int pst_jpeg_backend(void);    /* nvjpegBackend_t in use, -1 before the first call */
 int pst_jpeg_batch(pst_ctx *c, const uint8_t *const *host_blobs, const size_t *host_lens, int64_t n, int height,
                    int width, uint64_t dst, uint64_t stream);
+/* The same with the bitstreams left where the Parquet decode put them: image i is the `host_lens[i]` bytes at DEVICE
+ * address base + host_offs[i] (the host only holds the 12 bytes of (offset, length) per image).  Uses nvJPEG's
+ * device-bitstream backends: the hardware JPEG engines (NVJPEG_BACKEND_HARDWARE_DEVICE) when this GPU/driver exposes
+ * them, else GPU-assisted Huffman (NVJPEG_BACKEND_GPU_HYBRID_DEVICE).  pst_jpeg_device_backend() creates that handle on
+ * first use and returns its nvjpegBackend_t, or -1 when neither exists (callers then stage the blobs on the host). */
+int pst_jpeg_device_backend(void);
+int pst_jpeg_batch_device(pst_ctx *c, uint64_t base, const int64_t *host_offs, const int32_t *host_lens, int64_t n,
+                          int height, int width, uint64_t dst, uint64_t stream);
 
 /* K11: predicate masks.  in_set on an integer key column (petastorm/predicates.py:44-55): mask[i] = key[i] in set.
  * `set_sorted` is a sorted device array of int64. */

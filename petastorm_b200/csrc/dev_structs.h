@@ -74,6 +74,13 @@ struct DevPage {            // 64 bytes
 };
 static_assert(sizeof(DevPage) == 64, "DevPage must be 64 bytes");
 
+struct BaDictEntry {        // one entry of a BYTE_ARRAY dictionary: where its bytes lie in the arena
+    int64_t off;
+    int32_t len;
+    int32_t pad;
+};
+static_assert(sizeof(BaDictEntry) == 16, "BaDictEntry must be 16 bytes");
+
 struct DevCol {             // 96 bytes
     int32_t ptype;          // parquet physical type
     int32_t width;          // bytes per decoded value (BOOLEAN 1, INT96 12, FLBA n); BYTE_ARRAY: 0

@@ -592,10 +592,44 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
         }
         if (seen != c.num_values) throw std::runtime_error("page value counts do not add up to the chunk's num_values");
         if (dc.dict_page >= 0 && c.type == PST_BYTE_ARRAY) {
-            int64_t rel = align_up(scratch_cur, 16);
-            dict_index_rel[slot] = rel;
-            scratch_cur = rel + (int64_t)dc.dict_count * 16;
-            p->ba_dict_pages.push_back(dc.dict_page);
+            // {offset, length} of every dictionary entry: a serial walk over the length prefixes.  When the device
+            // receives the page uncompressed (stored that way, or literal-only Snappy) the planner walks it right here
+            // and ships the table with the raw region; otherwise k_ba_dict_index does it after decompression.
+            const HostPage &dp = p->pages[dc.dict_page];
+            std::vector<BaDictEntry> entries;
+            bool on_host = dp.d.codec == PST_CODEC_NONE && dc.dict_count <= 65536;
+            if (on_host) {
+                auto image_byte = [&](int64_t off) -> int {        // byte `off` of the page image, -1 behind its end
+                    if (dp.segs.empty()) return off < dp.d.comp_size ? f->map[dp.file_off + off] : -1;
+                    for (const auto &sg : dp.segs) {
+                        if (off < sg.second) return f->map[sg.first + off];
+                        off -= sg.second;
+                    }
+                    return -1;
+                };
+                int64_t pos = 0;
+                entries.reserve((size_t)dc.dict_count);
+                for (int i = 0; i < dc.dict_count && on_host; i++) {
+                    uint32_t len = 0;
+                    for (int b = 0; b < 4; b++) {
+                        const int v = image_byte(pos + b);
+                        if (v < 0) { on_host = false; break; }
+                        len |= (uint32_t)v << (8 * b);
+                    }
+                    pos += 4;
+                    if (!on_host || pos + (int64_t)len > (int64_t)dp.d.uncomp_size) { on_host = false; break; }
+                    entries.push_back(BaDictEntry{dp.d.img_off + pos, (int32_t)len, 0});
+                    pos += len;
+                }
+            }
+            if (on_host) {
+                p->host_dict_index.emplace_back(slot, std::move(entries));      // placed with the tables below
+            } else {      // (a malformed dictionary is left to the device kernel, which reports it)
+                int64_t rel = align_up(scratch_cur, 16);
+                dict_index_rel[slot] = rel;
+                scratch_cur = rel + (int64_t)dc.dict_count * 16;
+                p->ba_dict_pages.push_back(dc.dict_page);
+            }
         }
     }
 
@@ -635,7 +669,14 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
             const int64_t w = p->dcols[hp.d.col].width, per = (kCopyTileBytes / w) * w;
             n_tiles += ((int64_t)hp.d.num_values * w + per - 1) / per;
         }
-    p->frag_pos_off = align_up(p->copy_tiles_off + (int64_t)sizeof(CopyTile) * n_tiles, 16);
+    int64_t dict_tab_cur = align_up(p->copy_tiles_off + (int64_t)sizeof(CopyTile) * n_tiles, 16);
+    std::vector<int64_t> host_dict_off(p->host_dict_index.size());
+    for (size_t i = 0; i < p->host_dict_index.size(); i++) {
+        host_dict_off[i] = dict_tab_cur;
+        p->dcols[p->host_dict_index[i].first].dict_index_off = dict_tab_cur;
+        dict_tab_cur += (int64_t)sizeof(BaDictEntry) * (int64_t)p->host_dict_index[i].second.size();
+    }
+    p->frag_pos_off = align_up(dict_tab_cur, 16);
     p->page_flag_off = align_up(p->frag_pos_off + 4 * p->frag_pos_count, 16);
     p->raw_bytes = align_up(p->page_flag_off + 4 * (int64_t)p->multi_pages.size(), 256);
     p->scratch_off = p->raw_bytes;
@@ -718,6 +759,10 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
         memcpy(t + (p->index_list_off - p->tables_off), p->index_pages.data(), 4 * p->index_pages.size());
     if (!p->copy_tiles.empty())
         memcpy(t + (p->copy_tiles_off - p->tables_off), p->copy_tiles.data(), sizeof(CopyTile) * p->copy_tiles.size());
+    for (size_t i = 0; i < p->host_dict_index.size(); i++)
+        if (!p->host_dict_index[i].second.empty())
+            memcpy(t + (host_dict_off[i] - p->tables_off), p->host_dict_index[i].second.data(),
+                   sizeof(BaDictEntry) * p->host_dict_index[i].second.size());
     if (!p->frag_pos_host.empty())
         memcpy(t + (p->frag_pos_off - p->tables_off), p->frag_pos_host.data(), 4 * p->frag_pos_host.size());
 

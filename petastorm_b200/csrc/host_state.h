@@ -40,6 +40,8 @@ struct pst_plan {
     std::vector<int32_t> multi_pages;        // compressed pages with more than one fragment (indexed first)
     std::vector<int32_t> gzip_pages;         // page indices compressed with GZIP
     std::vector<int32_t> index_pages;        // multi-fragment pages whose fragment positions the device has to find
+    // BYTE_ARRAY dictionaries the planner indexed itself (pages the device sees uncompressed): entries per plan column
+    std::vector<std::pair<int, std::vector<pst::BaDictEntry>>> host_dict_index;
     std::vector<pst::CopyTile> copy_tiles;   // work items of k_copy_tiles (PF_COPY pages, <= 64 KiB each)
     int64_t unwrapped_pages = 0;             // literal-only Snappy pages delivered as uncompressed images
     int64_t host_indexed_pages = 0;          // multi-fragment Snappy pages whose fragment positions the planner found

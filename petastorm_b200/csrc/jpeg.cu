@@ -7,6 +7,7 @@
 #include <dlfcn.h>
 #include <nvjpeg.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -69,12 +70,31 @@ struct JpegState {
     nvjpegJpegState_t state = nullptr;
     int batch = 0;
     int backend = -1;
+    bool tried = false;
     std::mutex mu;
 };
 
 JpegState &jstate() {
     static JpegState s;
     return s;
+}
+// a second handle whose batched decode reads the bitstreams from DEVICE memory (no blob D2H)
+JpegState &jstate_device() {
+    static JpegState s;
+    return s;
+}
+
+void fill_outputs(std::vector<nvjpegImage_t> &outs, uint64_t dst, int64_t n, int height, int width) {
+    uint8_t *d = (uint8_t *)dst;
+    const size_t img_bytes = (size_t)height * width * 3;
+    for (int64_t i = 0; i < n; i++) {
+        for (int k = 0; k < NVJPEG_MAX_COMPONENT; k++) {
+            outs[i].channel[k] = nullptr;
+            outs[i].pitch[k] = 0;
+        }
+        outs[i].channel[0] = d + (size_t)i * img_bytes;
+        outs[i].pitch[0] = (size_t)width * 3;
+    }
 }
 
 }  // namespace
@@ -84,6 +104,69 @@ extern "C" {
 int pst_jpeg_available(void) { return api().ok ? 1 : 0; }
 
 int pst_jpeg_backend(void) { return jstate().backend; }
+
+int pst_jpeg_device_backend(void) {
+    // creates the device-bitstream handle on first use: the hardware JPEG engines first, then GPU-assisted Huffman
+    NvjpegApi &a = api();
+    if (!a.ok) return -1;
+    JpegState &js = jstate_device();
+    std::lock_guard<std::mutex> g(js.mu);
+    if (!js.tried) {
+        js.tried = true;
+        const char *skip_hw = getenv("PST_JPEG_NO_HW");
+        const nvjpegBackend_t order[] = {NVJPEG_BACKEND_HARDWARE_DEVICE, NVJPEG_BACKEND_GPU_HYBRID_DEVICE};
+        for (nvjpegBackend_t b : order) {
+            if (b == NVJPEG_BACKEND_HARDWARE_DEVICE && skip_hw && skip_hw[0] == '1') continue;
+            if (a.CreateEx(b, nullptr, nullptr, 0, &js.handle) == NVJPEG_STATUS_SUCCESS) {
+                if (a.JpegStateCreate(js.handle, &js.state) == NVJPEG_STATUS_SUCCESS) {
+                    js.backend = (int)b;
+                    break;
+                }
+                a.Destroy(js.handle);
+            }
+            js.handle = nullptr;
+        }
+    }
+    return js.backend;
+}
+
+int pst_jpeg_batch_device(pst_ctx *c, uint64_t base, const int64_t *host_offs, const int32_t *host_lens, int64_t n,
+                          int height, int width, uint64_t dst, uint64_t stream) {
+    (void)c;
+    try {
+        NvjpegApi &a = api();
+        if (!a.ok) throw std::runtime_error("nvJPEG unavailable: " + a.why);
+        if (n <= 0) return 0;
+        if (pst_jpeg_device_backend() < 0)
+            throw std::runtime_error("this nvJPEG has no backend that decodes device-resident bitstreams");
+        JpegState &js = jstate_device();
+        std::lock_guard<std::mutex> g(js.mu);
+        if (js.batch != (int)n) {
+            nvjpegStatus_t st = a.DecodeBatchedInitialize(js.handle, js.state, (int)n, 1, NVJPEG_OUTPUT_RGBI);
+            if (st != NVJPEG_STATUS_SUCCESS)
+                throw std::runtime_error("nvjpegDecodeBatchedInitialize (device bitstreams) failed " + std::to_string((int)st));
+            js.batch = (int)n;
+        }
+        std::vector<const unsigned char *> ptrs((size_t)n);
+        std::vector<size_t> lens((size_t)n);
+        for (int64_t i = 0; i < n; i++) {
+            ptrs[i] = (const unsigned char *)base + host_offs[i];
+            lens[i] = (size_t)host_lens[i];
+        }
+        std::vector<nvjpegImage_t> outs((size_t)n);
+        fill_outputs(outs, dst, n, height, width);
+        nvjpegStatus_t st = a.DecodeBatched(js.handle, js.state, ptrs.data(), lens.data(), outs.data(), (cudaStream_t)stream);
+        if (st != NVJPEG_STATUS_SUCCESS) {
+            js.batch = 0;
+            throw std::runtime_error("nvjpegDecodeBatched (device bitstreams, backend " + std::to_string(js.backend) +
+                                     ") failed with status " + std::to_string((int)st));
+        }
+        return 0;
+    } catch (const std::exception &e) {
+        pst::set_error(e.what());
+        return 1;
+    }
+}
 
 int pst_jpeg_batch(pst_ctx *c, const uint8_t *const *host_blobs, const size_t *host_lens, int64_t n, int height,
                    int width, uint64_t dst, uint64_t stream) {
@@ -129,16 +212,7 @@ int pst_jpeg_batch(pst_ctx *c, const uint8_t *const *host_blobs, const size_t *h
                                          ", expected " + std::to_string(height) + "x" + std::to_string(width));
         }
         std::vector<nvjpegImage_t> outs((size_t)n);
-        uint8_t *d = (uint8_t *)dst;
-        const size_t img_bytes = (size_t)height * width * 3;
-        for (int64_t i = 0; i < n; i++) {
-            for (int k = 0; k < NVJPEG_MAX_COMPONENT; k++) {
-                outs[i].channel[k] = nullptr;
-                outs[i].pitch[k] = 0;
-            }
-            outs[i].channel[0] = d + (size_t)i * img_bytes;
-            outs[i].pitch[0] = (size_t)width * 3;
-        }
+        fill_outputs(outs, dst, n, height, width);
         nvjpegStatus_t st = a.DecodeBatched(js.handle, js.state, host_blobs, host_lens, outs.data(), (cudaStream_t)stream);
         if (st != NVJPEG_STATUS_SUCCESS) {
             js.batch = 0;  // the batch state must be re-initialised after a failure

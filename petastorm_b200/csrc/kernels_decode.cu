@@ -875,12 +875,6 @@ k_snappy_index(const uint8_t *__restrict__ arena, const DevPage *__restrict__ pa
 // ---------------------------------------------------------------------------------------------------------------
 // K4 (BYTE_ARRAY dictionaries): {offset, len} of every entry of a PLAIN dictionary page.
 // ---------------------------------------------------------------------------------------------------------------
-struct BaDictEntry {
-    int64_t off;
-    int32_t len;
-    int32_t pad;
-};
-
 __global__ void k_ba_dict_index(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages,
                                 const DevCol *__restrict__ cols, const int32_t *__restrict__ list, int n_list,
                                 int32_t *status) {

@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #include "dev_structs.h"
+#include "dev_util.cuh"
 #include "kernels.h"
 
 namespace pst {
@@ -43,9 +44,16 @@ struct HuffD {
     uint16_t symbol[kMaxDCodes];
 };
 
+constexpr int kLutL = 10;      // primary bits of the literal/length lookup table
+constexpr int kLutD = 8;       // primary bits of the distance lookup table
+
 struct WarpState {
     Huff lencode;
     HuffD distcode;
+    // one-step decode tables: entry = (symbol << 4) | code length for codes of <= kLut* bits (index = the next stream
+    // bits, LSB first); 0 = longer code, decoded bit by bit from the canonical tables above
+    uint16_t lut_l[1 << kLutL];
+    uint16_t lut_d[1 << kLutD];
     uint16_t lengths[kMaxLCodes + kMaxDCodes + 2];
     uint8_t palette[256 * 3];
     // broadcast slots
@@ -115,6 +123,32 @@ __device__ __forceinline__ int bits_get(Bits &b, Src &s, int n) {
     return v;
 }
 
+// fills the bit buffer from the current IDAT payload without the per-byte segment checks (up to 7 bytes at once)
+__device__ __forceinline__ void bits_refill_fast(Bits &b, Src &s) {
+    while (b.cnt <= 56 && s.p < s.seg_end) {
+        b.buf |= (uint64_t)(*s.p++) << b.cnt;
+        b.cnt += 8;
+    }
+}
+
+// one-step tables from the canonical (count / symbol) representation: canonical codes are handed out in order of
+// (length, symbol); DEFLATE packs them MSB first into an LSB-first bit stream, hence the bit reversal
+template <typename H>
+__device__ void lut_build(const H &h, uint16_t *lut, int primary) {
+    for (int i = 0; i < (1 << primary); i++) lut[i] = 0;
+    int code = 0, index = 0;
+    for (int len = 1; len <= primary; len++) {
+        const int count = h.count[len];
+        for (int k = 0; k < count; k++) {
+            const uint32_t rev = __brev((uint32_t)(code + k)) >> (32 - len);
+            const uint16_t e = (uint16_t)((h.symbol[index + k] << 4) | len);
+            for (uint32_t j = rev; j < (1u << primary); j += 1u << len) lut[j] = e;
+        }
+        code = (code + count) << 1;
+        index += count;
+    }
+}
+
 // canonical Huffman decode, one bit at a time (count/symbol representation)
 template <typename H>
 __device__ int huff_decode(Bits &b, Src &s, const H &h) {
@@ -154,6 +188,20 @@ __device__ int huff_build(H &h, const uint16_t *length, int n) {
     return left;
 }
 
+// table-driven decode: one lookup for codes of <= `primary` bits, the bit-serial walk for the rare longer ones
+template <typename H>
+__device__ __forceinline__ int huff_decode_lut(Bits &b, Src &s, const H &h, const uint16_t *lut, int primary) {
+    if (b.cnt < kMaxBits) bits_refill_fast(b, s);
+    const uint16_t e = lut[b.buf & ((1u << primary) - 1)];
+    const int len = e & 15;
+    if (e != 0 && len <= b.cnt) {
+        b.buf >>= len;
+        b.cnt -= len;
+        return e >> 4;
+    }
+    return huff_decode(b, s, h);      // long code, or the tail of a segment (bits_need crosses IDAT boundaries)
+}
+
 __device__ __forceinline__ int paeth(int a, int b, int c) {
     int p = a + b - c;
     int pa = abs(p - a), pb = abs(p - b), pc = abs(p - c);
@@ -162,39 +210,11 @@ __device__ __forceinline__ int paeth(int a, int b, int c) {
     return c;
 }
 
-// DEFLATE blocks (RFC 1951) from the bit reader into raw[op ..), at most raw_total bytes; returns 0 or 1 (corrupt).
-// One lane; `ws` holds the Huffman tables of its warp.
-__device__ int deflate_blocks(Bits &b, Src &s, uint8_t *raw, int64_t raw_total, WarpState &ws, int64_t &op) {
+// One Huffman-coded block (type 1 fixed / type 2 dynamic), decoded by a single lane: table set-up, then
+// literal/length + distance symbols through the lookup tables until end-of-block.  Returns 0 or 1 (corrupt).
+__device__ int deflate_huffman_block(Bits &b, Src &s, uint8_t *raw, int64_t raw_total, WarpState &ws, int64_t &op, int type) {
     int err = 0;
-    int last = 0;
-    while (!err && !last) {
-        last = bits_get(b, s, 1);
-        int type = bits_get(b, s, 2);
-        if (last < 0 || type < 0) { err = 1; break; }
-        if (type == 0) {
-            // stored: drop bits to the byte boundary, LEN / NLEN, then raw bytes
-            b.buf = 0;
-            b.cnt = 0;  // bits_get refills byte-wise, so a partial byte is all that can be buffered... see note
-            int l0 = src_byte(s), l1 = src_byte(s), n0 = src_byte(s), n1 = src_byte(s);
-            if (l0 < 0 || l1 < 0 || n0 < 0 || n1 < 0) { err = 1; break; }
-            int len = l0 | (l1 << 8);
-            if ((len ^ 0xffff) != (n0 | (n1 << 8))) { err = 1; break; }
-            if (op + len > raw_total) { err = 1; break; }
-            while (len > 0) {
-                if (s.p == s.seg_end) {
-                    src_next_segment(s);
-                    if (s.eof) { err = 1; break; }
-                }
-                int64_t take = s.seg_end - s.p;
-                if (take > len) take = len;
-                for (int64_t i = 0; i < take; i++) raw[op + i] = s.p[i];
-                s.p += take;
-                op += take;
-                len -= (int)take;
-            }
-            continue;
-        }
-        if (type == 3) { err = 1; break; }
+    do {
         if (type == 1) {
             int sym = 0;
             for (; sym < 144; sym++) ws.lengths[sym] = 8;
@@ -251,9 +271,11 @@ __device__ int deflate_blocks(Bits &b, Src &s, uint8_t *raw, int64_t raw_total, 
             int e2 = huff_build(ws.distcode, ws.lengths + nlen, ndist);
             if (e2 < 0 || (e2 > 0 && ndist - ws.distcode.count[0] != 1)) { err = 1; break; }
         }
+        lut_build(ws.lencode, ws.lut_l, kLutL);
+        lut_build(ws.distcode, ws.lut_d, kLutD);
         // literal/length + distance codes
         for (;;) {
-            int sym = huff_decode(b, s, ws.lencode);
+            int sym = huff_decode_lut(b, s, ws.lencode, ws.lut_l, kLutL);
             if (sym < 0) { err = 1; break; }
             if (sym < 256) {
                 if (op >= raw_total) { err = 1; break; }
@@ -266,7 +288,7 @@ __device__ int deflate_blocks(Bits &b, Src &s, uint8_t *raw, int64_t raw_total, 
                 int eb = bits_get(b, s, c_len_extra[sym]);
                 if (eb < 0) { err = 1; break; }
                 int len = c_len_base[sym] + eb;
-                int ds = huff_decode(b, s, ws.distcode);
+                int ds = huff_decode_lut(b, s, ws.distcode, ws.lut_d, kLutD);
                 if (ds < 0 || ds >= 30) { err = 1; break; }
                 int de = bits_get(b, s, c_dist_extra[ds]);
                 if (de < 0) { err = 1; break; }
@@ -275,8 +297,142 @@ __device__ int deflate_blocks(Bits &b, Src &s, uint8_t *raw, int64_t raw_total, 
                 for (int i = 0; i < len; i++, op++) raw[op] = raw[op - dist];
             }
         }
+    } while (0);
+    return err;
+}
+
+__device__ __forceinline__ const uint8_t *shfl_ptr(const uint8_t *p, int src) {
+    const uint64_t v = (uint64_t)(uintptr_t)p;
+    const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src), hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+    return (const uint8_t *)(uintptr_t)(((uint64_t)hi << 32) | lo);
+}
+__device__ __forceinline__ int64_t shfl_i64(int64_t v, int src) {
+    const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src), hi = __shfl_sync(0xffffffffu, (uint32_t)((uint64_t)v >> 32), src);
+    return (int64_t)(((uint64_t)hi << 32) | lo);
+}
+
+// DEFLATE blocks (RFC 1951) from the bit reader into raw[op ..), at most raw_total bytes; returns 0 or 1 (corrupt),
+// uniformly across the warp.  Called by ALL 32 lanes of a warp: lane 0 owns the bit reader, the source cursor and `op`
+// (the other lanes' copies are ignored); the bit stream itself is serial, but
+//   * stored blocks (what zlib emits for incompressible data, e.g. every scanline of a noise image) are moved by the
+//     whole warp with 16-byte vector copies, and
+//   * Huffman blocks are decoded by lane 0 through one-step lookup tables (10 bits literal/length, 8 bits distance).
+// `ws` holds the tables of the warp.  The source must lie in a buffer with 16 bytes of slack on both sides (the arena).
+__device__ int deflate_blocks(Bits &b, Src &s, uint8_t *raw, int64_t raw_total, WarpState &ws, int64_t &op, int lane) {
+    int err = 0;
+    int last = 0;
+    while (!err && !last) {
+        int type = 0;
+        if (lane == 0) {
+            last = bits_get(b, s, 1);
+            type = bits_get(b, s, 2);
+            if (last < 0 || type < 0) err = 1;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        type = __shfl_sync(0xffffffffu, type, 0);
+        err = __shfl_sync(0xffffffffu, err, 0);
+        if (err) break;
+        if (type == 0) {
+            // stored: drop the bits up to the byte boundary, LEN / NLEN, then raw bytes
+            int len = 0;
+            if (lane == 0) {
+                const int drop = b.cnt & 7;
+                b.buf >>= drop;
+                b.cnt -= drop;
+                const int l = bits_get(b, s, 16), nl = bits_get(b, s, 16);
+                if (l < 0 || nl < 0 || (l ^ 0xffff) != nl || op + l > raw_total) err = 1;
+                else {
+                    len = l;
+                    // the table-driven decoder reads ahead: whole bytes still in the bit buffer are the first bytes of
+                    // the block; what follows comes straight from the source
+                    while (len > 0 && b.cnt >= 8) {
+                        raw[op++] = (uint8_t)(b.buf & 0xff);
+                        b.buf >>= 8;
+                        b.cnt -= 8;
+                        len--;
+                    }
+                }
+            }
+            err = __shfl_sync(0xffffffffu, err, 0);
+            if (err) break;
+            len = __shfl_sync(0xffffffffu, len, 0);
+            while (len > 0) {
+                const uint8_t *p = nullptr;
+                int take = 0;
+                if (lane == 0) {
+                    if (s.p == s.seg_end) {
+                        src_next_segment(s);
+                        if (s.eof) err = 1;
+                    }
+                    if (!err) {
+                        const int64_t avail = s.seg_end - s.p;
+                        take = avail > len ? len : (int)avail;
+                        p = s.p;
+                        s.p += take;
+                    }
+                }
+                err = __shfl_sync(0xffffffffu, err, 0);
+                if (err) break;
+                take = __shfl_sync(0xffffffffu, take, 0);
+                p = shfl_ptr(p, 0);
+                const int64_t o = shfl_i64(op, 0);
+                coop_copy(raw + o, p, take, lane, 32);
+                if (lane == 0) op += take;
+                len -= take;
+            }
+            __syncwarp();          // later back-references of lane 0 may read what the other lanes just wrote
+            continue;
+        }
+        if (type == 3) { err = 1; break; }
+        if (lane == 0) {
+            err = deflate_huffman_block(b, s, raw, raw_total, ws, op, type);
+        }
+        __syncwarp();
+        err = __shfl_sync(0xffffffffu, err, 0);
     }
     return err;
+}
+
+// PNG filter type 1 (Sub): recon[i] = filt[i] + recon[i - bpp] (mod 256) is a prefix sum per byte channel.  Every lane
+// scans its own run of 8 pixels, a warp scan adds the totals of the lanes in front of it, and a running carry links the
+// 256-pixel chunks of a scanline - instead of one lane per channel walking the whole line.
+template <int BPP>
+__device__ __forceinline__ void unfilter_sub(uint8_t *cur, int64_t nbytes, int lane) {
+    constexpr int K = 8;
+    const int64_t npix = nbytes / BPP;
+    uint32_t carry[BPP];
+#pragma unroll
+    for (int c = 0; c < BPP; c++) carry[c] = 0;
+    for (int64_t p0 = 0; p0 < npix; p0 += 32 * K) {
+        const int64_t my0 = p0 + (int64_t)lane * K;
+        const int cnt = (int)max((int64_t)0, min((int64_t)K, npix - my0));
+        uint8_t vals[K * BPP];
+        uint32_t loc[BPP];
+#pragma unroll
+        for (int c = 0; c < BPP; c++) loc[c] = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+#pragma unroll
+            for (int c = 0; c < BPP; c++) {
+                if (k < cnt) loc[c] = (loc[c] + cur[(my0 + k) * BPP + c]) & 255u;
+                vals[k * BPP + c] = (uint8_t)loc[c];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < BPP; c++) {
+            uint32_t incl = loc[c];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            const uint32_t add = (carry[c] + incl - loc[c]) & 255u;
+            carry[c] = (carry[c] + __shfl_sync(0xffffffffu, incl, 31)) & 255u;
+#pragma unroll
+            for (int k = 0; k < K; k++)
+                if (k < cnt) cur[(my0 + k) * BPP + c] = (uint8_t)((vals[k * BPP + c] + add) & 255u);
+        }
+    }
 }
 
 constexpr int kPngWarpsPerBlock = 2;
@@ -298,9 +454,15 @@ k_png_batch(const uint8_t *__restrict__ base, const int64_t *__restrict__ offs, 
     uint8_t *out = dst + img * out_bytes;
     uint8_t *raw = work + img * work_per_image;  // filtered scanlines: height * (1 + file_stride)
 
-    // ---- lane 0: header walk + inflate
+    // ---- lane 0: header walk; then the whole warp inflates (lane 0 owns the bit reader)
     int ctype = 0, depth = 0;
     int64_t file_stride = 0;  // bytes per scanline in the file (palette images: 1 byte per pixel)
+    Src s;
+    s.p = s.seg_end = s.blob_end = nullptr;
+    s.eof = false;
+    Bits b;
+    b.buf = 0;
+    b.cnt = 0;
     if (lane == 0) {
         int err = 0;
         ws.have_plte = 0;
@@ -308,10 +470,7 @@ k_png_batch(const uint8_t *__restrict__ base, const int64_t *__restrict__ offs, 
         if (blen < 8 + 25) err = DE_PNG_CORRUPT;
         for (int i = 0; i < 8 && !err; i++)
             if (blob[i] != sig[i]) err = DE_PNG_CORRUPT;
-        Src s;
         s.blob_end = blob + blen;
-        s.eof = false;
-        s.p = s.seg_end = nullptr;
         if (!err) {
             const uint8_t *q = blob + 8;
             if (be32(q) != 13 || be32(q + 4) != 0x49484452u) err = DE_PNG_CORRUPT;  // IHDR
@@ -358,23 +517,21 @@ k_png_batch(const uint8_t *__restrict__ base, const int64_t *__restrict__ offs, 
                 if (!err && ctype == 3 && !ws.have_plte) err = DE_PNG_CORRUPT;
             }
         }
-        ws.err = err;
-        // hand the source cursor to the inflate loop below through registers (lane 0 only)
         if (!err) {
-            const int64_t raw_total = (int64_t)height * (1 + file_stride);
-            Bits b;
-            b.buf = 0;
-            b.cnt = 0;
             int cmf = bits_get(b, s, 8), flg = bits_get(b, s, 8);
             if (cmf < 0 || flg < 0 || (cmf & 15) != 8 || ((cmf << 8) + flg) % 31 != 0 || (flg & 0x20)) err = DE_PNG_CORRUPT;
-            int64_t op = 0;
-            if (!err && deflate_blocks(b, s, raw, raw_total, ws, op)) err = DE_PNG_CORRUPT;
-            if (!err && op != raw_total) err = DE_PNG_CORRUPT;
-            ws.err = err;
         }
+        ws.err = err;
     }
     __syncwarp();
-    const int err = ws.err;
+    int err = ws.err;
+    file_stride = __shfl_sync(0xffffffffu, (int)file_stride, 0);
+    if (!err) {
+        const int64_t raw_total = (int64_t)height * (1 + file_stride);
+        int64_t op = 0;
+        if (deflate_blocks(b, s, raw, raw_total, ws, op, lane)) err = DE_PNG_CORRUPT;
+        else if (shfl_i64(op, 0) != raw_total) err = DE_PNG_CORRUPT;
+    }
     if (err) {
         if (lane == 0) {
             if (atomicCAS(status, 0, err) == 0) { status[1] = (int)img; status[2] = blen; }
@@ -385,7 +542,6 @@ k_png_batch(const uint8_t *__restrict__ base, const int64_t *__restrict__ offs, 
     }
     ctype = __shfl_sync(0xffffffffu, ctype, 0);
     depth = __shfl_sync(0xffffffffu, depth, 0);
-    file_stride = __shfl_sync(0xffffffffu, file_stride, 0);
     const int bpp = ctype == 3 ? 1 : channels * sample_bytes;
     const int64_t line = 1 + file_stride;
 
@@ -399,13 +555,10 @@ k_png_batch(const uint8_t *__restrict__ base, const int64_t *__restrict__ offs, 
             if (prior)
                 for (int64_t i = lane; i < file_stride; i += 32) cur[i] = (uint8_t)(cur[i] + prior[i]);
         } else if (ft == 1) {
-            if (lane < bpp) {
-                int a = 0;
-                for (int64_t i = lane; i < file_stride; i += bpp) {
-                    a = (cur[i] + a) & 255;
-                    cur[i] = (uint8_t)a;
-                }
-            }
+            if (bpp == 3) unfilter_sub<3>(cur, file_stride, lane);
+            else if (bpp == 1) unfilter_sub<1>(cur, file_stride, lane);
+            else if (bpp == 6) unfilter_sub<6>(cur, file_stride, lane);
+            else unfilter_sub<2>(cur, file_stride, lane);
         } else if (ft == 3) {
             if (lane < bpp) {
                 int a = 0;
@@ -480,47 +633,62 @@ k_gzip_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, con
         for (int64_t i = lane; i < lv; i += 32) dst[i] = src[i];
         src += lv; dst += lv; src_n -= lv; dst_n -= lv;
     }
-    if (lane != 0 || src_n <= 0) return;
+    if (src_n <= 0) return;
+    // the whole warp walks the members; lane 0 owns the cursor (its err / op are broadcast where the flow depends on them)
     Src s;
     s.p = src;
     s.seg_end = s.blob_end = src + src_n;
     s.eof = true;                       // a single segment: the reader never looks for a next one
     int err = 0;
     int64_t op = 0;
-    while (!err && op < dst_n) {        // members may be concatenated
-        if (s.seg_end - s.p < 18) { err = 1; break; }
-        const uint8_t *h = s.p;
-        const int flg = h[3];
-        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || (flg & 0xe0)) { err = 2; break; }
-        s.p += 10;
-        if (flg & 4) {                  // FEXTRA
-            if (s.seg_end - s.p < 2) { err = 1; break; }
-            const int xlen = s.p[0] | (s.p[1] << 8);
-            s.p += 2;
-            if (s.seg_end - s.p < xlen) { err = 1; break; }
-            s.p += xlen;
-        }
-        for (int f = 8; f <= 16 && !err; f <<= 1) {   // FNAME, FCOMMENT: zero-terminated
-            if (!(flg & f)) continue;
-            while (s.p < s.seg_end && *s.p) s.p++;
-            if (s.p >= s.seg_end) err = 1; else s.p++;
-        }
-        if (!err && (flg & 2)) {        // FHCRC
-            if (s.seg_end - s.p < 2) err = 1; else s.p += 2;
-        }
-        if (err) break;
+    for (;;) {                          // members may be concatenated
+        if (shfl_i64(op, 0) >= dst_n) break;
         Bits b;
         b.buf = 0;
         b.cnt = 0;
-        const int64_t before = op;
-        if (deflate_blocks(b, s, dst, dst_n, ws, op)) { err = 3; break; }
-        if (s.seg_end - s.p < 8) { err = 1; break; }      // CRC32 (not verified), ISIZE
-        const uint32_t isize = (uint32_t)s.p[4] | ((uint32_t)s.p[5] << 8) | ((uint32_t)s.p[6] << 16) | ((uint32_t)s.p[7] << 24);
-        if (isize != (uint32_t)(op - before)) { err = 4; break; }
-        s.p += 8;
+        if (lane == 0) {
+            do {
+                if (s.seg_end - s.p < 18) { err = 1; break; }
+                const uint8_t *h = s.p;
+                const int flg = h[3];
+                if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || (flg & 0xe0)) { err = 2; break; }
+                s.p += 10;
+                if (flg & 4) {                  // FEXTRA
+                    if (s.seg_end - s.p < 2) { err = 1; break; }
+                    const int xlen = s.p[0] | (s.p[1] << 8);
+                    s.p += 2;
+                    if (s.seg_end - s.p < xlen) { err = 1; break; }
+                    s.p += xlen;
+                }
+                for (int f = 8; f <= 16 && !err; f <<= 1) {   // FNAME, FCOMMENT: zero-terminated
+                    if (!(flg & f)) continue;
+                    while (s.p < s.seg_end && *s.p) s.p++;
+                    if (s.p >= s.seg_end) err = 1; else s.p++;
+                }
+                if (!err && (flg & 2)) {        // FHCRC
+                    if (s.seg_end - s.p < 2) err = 1; else s.p += 2;
+                }
+            } while (0);
+        }
+        err = __shfl_sync(0xffffffffu, err, 0);
+        if (err) break;
+        const int64_t before = shfl_i64(op, 0);
+        if (deflate_blocks(b, s, dst, dst_n, ws, op, lane)) { err = 3; break; }
+        if (lane == 0) {
+            // the bit reader may have read ahead: whole bytes left in its buffer belong to the trailer
+            s.p -= b.cnt >> 3;
+            if (s.seg_end - s.p < 8) err = 1;      // CRC32 (not verified), ISIZE
+            else {
+                const uint32_t isize = (uint32_t)s.p[4] | ((uint32_t)s.p[5] << 8) | ((uint32_t)s.p[6] << 16) | ((uint32_t)s.p[7] << 24);
+                if (isize != (uint32_t)(op - before)) err = 4;
+                s.p += 8;
+            }
+        }
+        err = __shfl_sync(0xffffffffu, err, 0);
+        if (err) break;
     }
-    if (!err && op != dst_n) err = 5;
-    if (err && atomicCAS(status, 0, (int)DE_GZIP_CORRUPT) == 0) { status[1] = pi; status[2] = err; }
+    if (!err && shfl_i64(op, 0) != dst_n) err = 5;
+    if (lane == 0 && err && atomicCAS(status, 0, (int)DE_GZIP_CORRUPT) == 0) { status[1] = pi; status[2] = err; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -536,12 +704,13 @@ k_zip_inflate_batch(const uint8_t *__restrict__ base, const int64_t *__restrict_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpState &ws = wstate[warp];
     const int64_t i = (int64_t)blockIdx.x * kPngWarpsPerBlock + warp;
-    if (i >= n || lane != 0) return;
+    if (i >= n) return;
     const int64_t r = row_idx ? row_idx[i] : i;
     const uint8_t *blob = base + offs[r];
     const int64_t blen = lens[r];
     uint8_t *out = dst + i * member_bytes;
     int err = 0;
+    // (every lane reads the same few header bytes: the flow below stays uniform across the warp)
     auto u16 = [&](int o) { return (int)blob[o] | ((int)blob[o + 1] << 8); };
     if (blen < 30 || blob[0] != 'P' || blob[1] != 'K' || blob[2] != 3 || blob[3] != 4) err = 1;
     else if (u16(6) & 1) err = 2;                            // encrypted
@@ -558,16 +727,16 @@ k_zip_inflate_batch(const uint8_t *__restrict__ base, const int64_t *__restrict_
             b.buf = 0;
             b.cnt = 0;
             int64_t op = 0;
-            if (deflate_blocks(b, s, out, member_bytes, ws, op)) err = 3;
-            else if (op != member_bytes) err = 4;
+            if (deflate_blocks(b, s, out, member_bytes, ws, op, lane)) err = 3;
+            else if (shfl_i64(op, 0) != member_bytes) err = 4;
         } else if (method == 0) {
             if (data_off + member_bytes > blen) err = 4;
-            else for (int64_t k = 0; k < member_bytes; k++) out[k] = blob[data_off + k];
+            else coop_copy(out, blob + data_off, member_bytes, lane, 32);
         } else {
             err = 5;
         }
     }
-    if (err && atomicCAS(status, 0, (int)DE_ZIP_CORRUPT) == 0) { status[1] = (int)i; status[2] = err; }
+    if (lane == 0 && err && atomicCAS(status, 0, (int)DE_ZIP_CORRUPT) == 0) { status[1] = (int)i; status[2] = err; }
 }
 
 }  // namespace

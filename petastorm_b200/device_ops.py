@@ -235,3 +235,23 @@ def jpeg_batch(host_blobs, height, width, device):
     torch.cuda.current_stream().synchronize()
     del keep
     return out
+
+
+def jpeg_batch_device(col, host_offs, host_lens, height, width):
+    """JPEG streams of a BYTE_ARRAY column decoded where they are: ``host_offs`` / ``host_lens`` are the (arena offset,
+    length) of the selected values as host numpy arrays (int64 / int32); the bitstreams never leave HBM (K9 through
+    nvJPEG's device-bitstream backend)."""
+    n = len(host_offs)
+    out = torch.empty((n, height, width, 3), dtype=torch.uint8, device=col.arena.device)
+    if n == 0:
+        return out
+    host_offs = np.ascontiguousarray(host_offs, dtype=np.int64)
+    host_lens = np.ascontiguousarray(host_lens, dtype=np.int32)
+    check(lib.pst_jpeg_batch_device(None, col.arena.data_ptr(), host_offs.ctypes.data, host_lens.ctypes.data, n, height,
+                                    width, out.data_ptr(), _stream()), 'jpeg_batch_device')
+    return out
+
+
+def jpeg_device_backend():
+    """nvjpegBackend_t of the device-bitstream handle (5 hardware engines, 4 GPU-assisted Huffman), -1 when unavailable."""
+    return int(lib.pst_jpeg_device_backend())

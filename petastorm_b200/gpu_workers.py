@@ -18,7 +18,7 @@ from decimal import Decimal
 import numpy as np
 import torch
 
-from petastorm_b200 import device_ops, rowgroup
+from petastorm_b200 import device_ops, native, rowgroup
 from petastorm_b200.cache import NullCache
 from petastorm_b200.codecs import (CompressedImageCodec, CompressedNdarrayCodec, NdarrayCodec, ScalarCodec,
                                    parse_npy_header)
@@ -32,6 +32,10 @@ _TORCH_OF_NUMPY = {np.dtype('uint8'): torch.uint8, np.dtype('int8'): torch.int8,
                    np.dtype('uint16'): torch.uint16, np.dtype('int32'): torch.int32, np.dtype('uint32'): torch.uint32,
                    np.dtype('int64'): torch.int64, np.dtype('uint64'): torch.uint64, np.dtype('float16'): torch.float16,
                    np.dtype('float32'): torch.float32, np.dtype('float64'): torch.float64, np.dtype('bool'): torch.bool}
+
+
+#: test hook: force the host-staged JPEG path even when nvJPEG can read device bitstreams
+_FORCE_HOST_JPEG = [False]
 
 
 class ScalarColumn(object):
@@ -816,7 +820,13 @@ class GpuPyDictWorker(_GpuWorkerBase):
         piece = self._split_pieces[piece_index]
         self._check_cache_usage(worker_predicate, shuffle_row_drop_partition)
         if worker_predicate:
-            rows = self._load_rows_with_predicate(piece, worker_predicate, shuffle_row_drop_partition)
+            # the predicate columns are decoded and evaluated here (the count decides whether the payload is read at
+            # all: upstream's early exit, py_dict_reader_worker.py:234-236); the payload columns of the matching rows
+            # are issued asynchronously and resolved by the consumer, like a row-group without a predicate
+            pending = self._load_rows_with_predicate(piece, worker_predicate, shuffle_row_drop_partition, defer=True)
+            if pending is not None:
+                self.publish_func(pending)
+            return
         elif isinstance(self._local_cache, NullCache):
             pending = self._issue_rows(piece, shuffle_row_drop_partition)   # asynchronous, resolved by the consumer
             if pending.num_rows:
@@ -1038,16 +1048,48 @@ class GpuPyDictWorker(_GpuWorkerBase):
         return result
 
     def _decode_jpeg(self, col, field, live):
+        """JPEG column -> ``[n, H, W, 3]`` RGB through nvJPEG.  The bitstreams stay in HBM (the Parquet decode left every
+        blob in the arena): the host reads the 12 bytes of (offset, length) per image and the first bytes of every
+        stream (SOF marker: geometry), and hands nvJPEG device pointers.  Without a device-bitstream backend the blobs
+        are staged through the host (the GPU still decodes)."""
         if len(live) == 0:
             return []
+        live = np.asarray(live)
+        if device_ops.jpeg_device_backend() < 0 or _FORCE_HOST_JPEG[0]:
+            return self._decode_jpeg_host_staged(col, field, live)
+        offs = col.offs.cpu().numpy()[live]
+        lens = col.lens.cpu().numpy()[live]
+        # geometry of every stream from its SOF marker (nvJPEG writes what the stream says: the output buffers must fit)
+        hw = _jpeg_sizes(device_ops.blob_prefix(col, 1024).cpu().numpy()[live])
+        shape = field.shape
+        if shape and None not in shape and len(shape) == 3 and shape[2] == 3:
+            bad = np.nonzero((hw[:, 0] != shape[0]) | (hw[:, 1] != shape[1]))[0]
+            if len(bad):
+                raise ValueError('JPEG {} is {}x{}, expected {}x{}'.format(int(bad[0]), int(hw[bad[0], 0]),
+                                                                          int(hw[bad[0], 1]), shape[0], shape[1]))
+        uniq = np.unique(hw, axis=0)
+        dims = {(int(h), int(w)): np.nonzero((hw[:, 0] == h) & (hw[:, 1] == w))[0] for h, w in uniq}
+        try:
+            if len(dims) == 1:
+                (h, w), _ = next(iter(dims.items()))
+                return device_ops.jpeg_batch_device(col, offs, lens, h, w)
+            result = [None] * len(live)
+            for (h, w), pos in dims.items():
+                out = device_ops.jpeg_batch_device(col, offs[pos], lens[pos], h, w)
+                for k, p in enumerate(pos):
+                    result[p] = out[k]
+            return result
+        except native.NativeLibraryError:
+            # e.g. a progressive stream the hardware engines refuse: the host-staged backend reports precise errors
+            return self._decode_jpeg_host_staged(col, field, live)
+
+    def _decode_jpeg_host_staged(self, col, field, live):
         blobs = rowgroup.gather_blobs_to_host(col, live)
         shape = field.shape
         if shape and None not in shape and len(shape) == 3 and shape[2] == 3:
             return device_ops.jpeg_batch(blobs, shape[0], shape[1], col.arena.device)
         # variable geometry: group by the SOF dimensions
-        dims = []
-        for b in blobs:
-            dims.append(_jpeg_size(b))
+        dims = [_jpeg_size(b) for b in blobs]
         result = [None] * len(blobs)
         for d in set(dims):
             pos = [i for i, x in enumerate(dims) if x == d]
@@ -1112,12 +1154,15 @@ class GpuPyDictWorker(_GpuWorkerBase):
             cols.pop(name, None)
         return cols
 
-    def _load_rows_with_predicate(self, piece, worker_predicate, shuffle_row_drop_partition):
+    def _load_rows_with_predicate(self, piece, worker_predicate, shuffle_row_drop_partition, defer=False):
+        """Two-phase read (petastorm/py_dict_reader_worker.py:216-262): predicate columns, mask, then the other columns
+        of the matching rows only.  With ``defer`` phase two is only *issued* (H2D + page decode queued on a decode
+        stream) and a :class:`PendingRowGroup` is returned whose resolution builds the columns - the payload transfer
+        of this row-group then overlaps the consumer's work on the previous one.  None when nothing matches."""
         predicate_fields, all_names = self._validate_predicate_fields(worker_predicate, self._schema)
         # partition columns ride along with every read upstream (legacy pyarrow appended them to each piece.read), so
         # they stay in the second read's field set; _read_raw serves them from the piece's partition keys
         other_names = all_names - predicate_fields
-        decoder = self._get_decoder()
         raw_p = self._read_raw(piece, predicate_fields)
         order = self._row_order(raw_p.num_rows, shuffle_row_drop_partition,
                                 self._ngram.length if self._ngram else 0)
@@ -1138,15 +1183,23 @@ class GpuPyDictWorker(_GpuWorkerBase):
                                                         torch.from_numpy(keep_host.astype(np.int64)).to(v.device))
                 else:
                     cols[name] = [v[i] for i in keep_host]
-            raw_o = None
-            if other_names:
-                raw_o = self._read_raw(piece, other_names)
-                cols.update(self._decode_all(raw_o, sorted(other_names), sel))
-            if self._transform_spec:
-                cols = self._apply_transform(cols, len(keep_host))
-            done = torch.cuda.Event()
-            done.record()
-        return GpuRowGroupRows(cols, len(keep_host), [_EventWaiter(done), raw_p.decoded, raw_o.decoded if raw_o else None])
+            phase1 = torch.cuda.Event()
+            phase1.record()
+        raw_o = self._read_raw(piece, other_names) if other_names else None    # issued, not waited for
+
+        def finalize():
+            with torch.cuda.stream(self._stream_of(raw_p)):
+                if raw_o is not None:
+                    cols.update(self._decode_all(raw_o, sorted(other_names), sel))
+                out = self._apply_transform(cols, len(keep_host)) if self._transform_spec else cols
+                done = torch.cuda.Event()
+                done.record()
+            return GpuRowGroupRows(out, len(keep_host),
+                                   [_EventWaiter(done), raw_p.decoded, raw_o.decoded if raw_o else None])
+
+        if defer:
+            return PendingRowGroup(lambda: self._finish_rows(finalize()), len(keep_host))
+        return finalize()
 
     def _predicate_mask(self, predicate, raw, pcols, order, count):
         """Boolean host mask of the rows to keep.  Device form when the predicate has one for these columns."""
@@ -1249,6 +1302,41 @@ def _npy_header_len(prefix):
     if prefix[6] == 1:
         return int.from_bytes(prefix[8:10], 'little') + 10
     return int.from_bytes(prefix[8:12], 'little') + 12
+
+
+def _jpeg_sizes(heads):
+    """(height, width) of n JPEG streams from their first bytes (uint8 [n, k]).  Streams written by one encoder share
+    their header layout, so the SOF position of the first stream is tried on all of them at once; the rest is parsed
+    one by one."""
+    n = len(heads)
+    out = np.zeros((n, 2), dtype=np.int64)
+    todo = np.arange(n)
+    if n:
+        b = heads[0].tobytes()
+        i = 2
+        pos = -1
+        while i + 9 < len(b):
+            if b[i] != 0xFF:
+                i += 1
+                continue
+            m = b[i + 1]
+            if m in (0xC0, 0xC1, 0xC2):
+                pos = i
+                break
+            if m in (0xD8, 0x01) or 0xD0 <= m <= 0xD7:
+                i += 2
+                continue
+            i += 2 + int.from_bytes(b[i + 2:i + 4], 'big')
+        if pos >= 0 and pos + 9 <= heads.shape[1]:
+            same = (heads[:, pos] == 0xFF) & np.isin(heads[:, pos + 1], (0xC0, 0xC1, 0xC2)) & \
+                (heads[:, :pos] == heads[0, :pos]).all(axis=1)
+            h16 = heads[:, pos + 5].astype(np.int64) * 256 + heads[:, pos + 6]
+            w16 = heads[:, pos + 7].astype(np.int64) * 256 + heads[:, pos + 8]
+            out[same, 0], out[same, 1] = h16[same], w16[same]
+            todo = np.nonzero(~same)[0]
+    for i in todo:
+        out[i] = _jpeg_size(heads[i].tobytes())
+    return out
 
 
 def _jpeg_size(blob):

@@ -113,6 +113,8 @@ _sig('pst_png_batch', c_int, c_uint64, c_uint64, c_uint64, c_uint64, c_int64, c_
 _sig('pst_jpeg_available', c_int)
 _sig('pst_jpeg_backend', c_int)
 _sig('pst_jpeg_batch', c_int, c_void_p, POINTER(c_void_p), POINTER(c_size_t), c_int64, c_int, c_int, c_uint64, c_uint64)
+_sig('pst_jpeg_device_backend', c_int)
+_sig('pst_jpeg_batch_device', c_int, c_void_p, c_uint64, c_void_p, c_void_p, c_int64, c_int, c_int, c_uint64, c_uint64)
 _sig('pst_mask_in_set_i64', c_int, c_uint64, c_int, c_int, c_int64, c_uint64, c_int64, c_uint64, c_uint64)
 _sig('pst_mask_md5_split_i64', c_int, c_uint64, c_int, c_int, c_int64, c_double, c_double, c_uint64, c_uint64)
 _sig('pst_compact_tmp_bytes', c_int64, c_int64)
@@ -132,7 +134,7 @@ EXPORTED = [
     'pst_plan_get_page', 'pst_plan_get_copy_tile',
     'pst_ctx_create', 'pst_ctx_destroy', 'pst_ctx_stats_json', 'pst_ctx_set_pinned_cache_bytes', 'pst_plan_upload', 'pst_plan_decode', 'pst_plan_decode_timed',
     'pst_nullable_to_f64', 'pst_narrow_int32', 'pst_gather_rows', 'pst_npy_batch', 'pst_blob_prefix', 'pst_zip_inflate_batch', 'pst_png_work_bytes',
-    'pst_png_batch', 'pst_jpeg_available', 'pst_jpeg_backend', 'pst_jpeg_batch', 'pst_mask_in_set_i64',
+    'pst_png_batch', 'pst_jpeg_available', 'pst_jpeg_backend', 'pst_jpeg_batch', 'pst_jpeg_device_backend', 'pst_jpeg_batch_device', 'pst_mask_in_set_i64',
     'pst_mask_md5_split_i64', 'pst_compact_tmp_bytes', 'pst_mask_compact', 'pst_normalize',
     'pst_ngram_valid_starts', 'pst_ngram_gather', 'pst_sanitize', 'pst_list_uniform',
 ]
