@@ -660,21 +660,47 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
 // then needs one shared-memory load and two adds per 16 elements.  Positions holding a slow-path tag, behind the window
 // or behind the stream have {0, 0}, which stalls the chain there.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kIdxBuilders = 4;
+// Builders per CTA.  A builder warp needs ~6.4k cycles per 1 KiB window, the walker ~0.6k: with four builders (the first
+// version, named barriers) a 1 MiB page took 0.84 ms and the sixteen dictionary pages of the C2 int64 columns set the
+// latency of the whole launch; twelve builders make the walker the limit.  The hand-over uses mbarriers in shared memory
+// (one full / one empty barrier per builder): named barriers are limited to 16 per CTA.
+constexpr int kIdxBuilders = 12;
 constexpr int kIdxThreads = 32 * (kIdxBuilders + 1);
 constexpr int kIdxW = 1024;
 constexpr int kIdxPad = 64;
-constexpr int kIdxRounds = 4;          // a table entry covers 2^kIdxRounds elements (5 was measured: the builders become
-                                       // the bottleneck, 0.90 ms instead of 0.84 ms per row-group)
-constexpr int kBarIdxFull = 1;                    // + builder : builder arrives, walker syncs
-constexpr int kBarIdxEmpty = 1 + kIdxBuilders;    // + builder : walker arrives, builder syncs
+constexpr int kIdxRounds = 6;          // a table entry covers 2^kIdxRounds elements: the walker (the serial part) does one
+                                       // shared-memory load per 64 elements; the twelve builders absorb the extra rounds
+constexpr size_t kIdxSmemBytes = (size_t)2 * kIdxBuilders * (kIdxW + kIdxPad) * sizeof(uint32_t);
+
+__device__ __forceinline__ void idx_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void idx_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void idx_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
+}
 
 __global__ void __launch_bounds__(kIdxThreads)
 k_snappy_index(const uint8_t *__restrict__ arena, const DevPage *__restrict__ pages,
                const int32_t *__restrict__ multi_list, int n_multi, uint32_t *__restrict__ frag_pos,
                uint32_t *__restrict__ page_flag) {
-    __shared__ __align__(16) uint32_t tab[kIdxBuilders][kIdxW + kIdxPad];
-    __shared__ __align__(16) uint32_t tmp[kIdxBuilders][kIdxW + kIdxPad];
+    extern __shared__ __align__(16) uint8_t idx_smem[];
+    uint32_t (*tab)[kIdxW + kIdxPad] = reinterpret_cast<uint32_t (*)[kIdxW + kIdxPad]>(idx_smem);
+    uint32_t (*tmp)[kIdxW + kIdxPad] = tab + kIdxBuilders;
+    __shared__ __align__(8) uint64_t bar_full[kIdxBuilders], bar_empty[kIdxBuilders];
     __shared__ uint32_t lut[256];                  // tag -> (bytes consumed * 4) | (bytes produced << 16); 0 = slow path
     __shared__ volatile uint32_t walker_ip;        // lower bound of the walker's position (lets builders skip windows)
     __shared__ volatile uint32_t give_up;
@@ -708,7 +734,15 @@ k_snappy_index(const uint8_t *__restrict__ arena, const DevPage *__restrict__ pa
         tab[t / kIdxPad][kIdxW + t % kIdxPad] = 0;
         tmp[t / kIdxPad][kIdxW + t % kIdxPad] = 0;
     }
-    if (threadIdx.x == 0) { walker_ip = in_begin; give_up = 0; }
+    if (threadIdx.x == 0) {
+        walker_ip = in_begin;
+        give_up = 0;
+        for (int b = 0; b < kIdxBuilders; b++) {
+            idx_mbar_init((uint32_t)__cvta_generic_to_shared(&bar_full[b]), 1);
+            idx_mbar_init((uint32_t)__cvta_generic_to_shared(&bar_empty[b]), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
     __syncthreads();
     const uint32_t nwin = (in_end + kIdxW - 1) / kIdxW;      // windows over positions [0, in_end), aligned to kIdxW
 
@@ -716,8 +750,11 @@ k_snappy_index(const uint8_t *__restrict__ arena, const DevPage *__restrict__ pa
         // ============================================ builders ===================================================
         const uint32_t tab_s = shared_addr(&tab[warp][0]), tmp_s = shared_addr(&tmp[warp][0]);
         const uint32_t lut_s = shared_addr(&lut[0]);
-        for (uint32_t j = (uint32_t)warp; j < nwin; j += kIdxBuilders) {
-            if (j >= (uint32_t)kIdxBuilders) named_bar_sync<kBarIdxEmpty, kIdxBuilders>(warp);
+        const uint32_t my_full = (uint32_t)__cvta_generic_to_shared(&bar_full[warp]);
+        const uint32_t my_empty = (uint32_t)__cvta_generic_to_shared(&bar_empty[warp]);
+        uint32_t use = 0;          // how often this builder's table slot has been filled
+        for (uint32_t j = (uint32_t)warp; j < nwin; j += kIdxBuilders, use++) {
+            if (use) idx_mbar_wait(my_empty, (use - 1) & 1u);      // the walker is done with the previous window of the slot
             const uint32_t w0 = j * kIdxW;
             const bool skip = __shfl_sync(0xffffffffu, (int)(give_up != 0 || w0 + kIdxW <= walker_ip), 0) != 0;
             if (!skip) {
@@ -772,8 +809,8 @@ k_snappy_index(const uint8_t *__restrict__ arena, const DevPage *__restrict__ pa
                     const uint32_t t = from_s; from_s = to_s; to_s = t;
                 }
             }
-            __threadfence_block();
-            named_bar_arrive<kBarIdxFull, kIdxBuilders>(warp);
+            __syncwarp();
+            if (lane == 0) idx_mbar_arrive(my_full);       // release: the table of window j is complete
         }
     } else {
         // ============================================ walker =====================================================
@@ -796,7 +833,7 @@ k_snappy_index(const uint8_t *__restrict__ arena, const DevPage *__restrict__ pa
         }
         for (uint32_t j = 0; j < nwin; j++) {
             const int b = (int)(j % kIdxBuilders);
-            named_bar_sync<kBarIdxFull, kIdxBuilders>(b);
+            idx_mbar_wait((uint32_t)__cvta_generic_to_shared(&bar_full[b]), (j / kIdxBuilders) & 1u);
             const uint32_t wend = min((j + 1) * (uint32_t)kIdxW, in_end);
             if (lane == 0 && !flag && ip < wend) {
                 const uint32_t base = shared_addr(&tab[b][0]) - ((j * (uint32_t)kIdxW) << 2);
@@ -859,10 +896,9 @@ k_snappy_index(const uint8_t *__restrict__ arena, const DevPage *__restrict__ pa
                 if (flag) give_up = 1;
             }
             if (lane == 0) walker_ip = ip;
-            if (j + kIdxBuilders < nwin) {
-                __threadfence_block();
-                named_bar_arrive<kBarIdxEmpty, kIdxBuilders>(b);
-            }
+            __syncwarp();
+            if (lane == 0 && j + kIdxBuilders < nwin)
+                idx_mbar_arrive((uint32_t)__cvta_generic_to_shared(&bar_empty[b]));
         }
         if (lane == 0) {
             if (!flag && (ip != in_end || op != dst_n || k != (uint32_t)pg.nfrag)) flag = 1;
@@ -1189,6 +1225,42 @@ k_decode_pages(uint8_t *__restrict__ arena, uint8_t *__restrict__ out, const Dev
 
     const uint8_t *dict = col.dict_img_off >= 0 ? arena + col.dict_img_off : nullptr;
     const BaDictEntry *ba_dict = col.dict_index_off >= 0 ? reinterpret_cast<const BaDictEntry *>(arena + col.dict_index_off) : nullptr;
+
+    // ---- fast path: dictionary-encoded 4/8-byte values of a flat page without nulls (what pyarrow writes for the first
+    // ~1 MiB of distinct values of every column before it falls back to PLAIN).  Thread 0 scans up to 256 run headers of
+    // the index stream at once (a 20,000-value page is ~40 bit-packed runs), then every thread extracts its indices
+    // straight from the page image and gathers from the dictionary: two block barriers per page instead of ~10 per
+    // 1024-value tile, no staging of indices or ranks through shared memory.
+    if (dict_enc && all_valid && col.max_rep == 0 && (W == 4 || W == 8) && dict != nullptr) {
+        uint32_t done = 0;
+        const uint32_t dict_count = (uint32_t)col.dict_count;
+        while (done < nvals) {
+            __syncthreads();
+            if (tid == 0) hybrid_scan(sh.idx_c, sh.table, nvals - done);
+            __syncthreads();
+            if (sh.idx_c.error || sh.table.filled == 0) {
+                if (tid == 0) report_error(status, DE_LEVELS_CORRUPT, pi, 12);
+                return;
+            }
+            const int n = sh.table.n;
+            const uint32_t filled = sh.table.filled;
+            const int bw = sh.idx_c.bw;
+            int ei = 0;
+            for (uint32_t i = tid; i < filled; i += kDecThreads) {
+                while (ei + 1 < n && sh.table.e[ei + 1].out_start <= i) ei++;
+                const RunEntry &e = sh.table.e[ei];
+                uint32_t di = e.is_rle ? e.value_or_index
+                                       : extract_bits(e.ptr, (uint64_t)(e.value_or_index + (i - e.out_start)) * bw, bw);
+                if (di >= dict_count) { report_error(status, DE_DICT_INDEX_RANGE, pi, (int)di); di = 0; }
+                const int64_t row = first + done + i;
+                if (W == 4) reinterpret_cast<uint32_t *>(o_values)[row] = reinterpret_cast<const uint32_t *>(dict)[di];
+                else reinterpret_cast<uint64_t *>(o_values)[row] = reinterpret_cast<const uint64_t *>(dict)[di];
+            }
+            done += filled;
+        }
+        if (o_valid) coop_fill(o_valid + first, 1, nvals, tid, kDecThreads);
+        return;
+    }
     const bool val_aligned = W > 0 && (((uintptr_t)val_ptr) % (W == 8 ? 8 : 4)) == 0;
 
     uint32_t rank_base = 0;  // valid values consumed before this tile
@@ -1321,13 +1393,15 @@ cudaError_t configure_decode_kernels() {
     e = cudaFuncSetAttribute(k_snappy_index, cudaFuncAttributePreferredSharedMemoryCarveout,
                              (int)cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_snappy_index, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kIdxSmemBytes);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_decode_pages, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeShared));
 }
 
 cudaError_t launch_snappy_index(uint8_t *arena, const DevPage *pages, const int32_t *multi_list, int n_multi,
                                 uint32_t *frag_pos, uint32_t *page_flag, cudaStream_t s) {
     if (n_multi <= 0) return cudaSuccess;
-    k_snappy_index<<<n_multi, kIdxThreads, 0, s>>>(arena, pages, multi_list, n_multi, frag_pos, page_flag);
+    k_snappy_index<<<n_multi, kIdxThreads, kIdxSmemBytes, s>>>(arena, pages, multi_list, n_multi, frag_pos, page_flag);
     return cudaGetLastError();
 }
 

@@ -68,12 +68,12 @@ struct WideShared {
     uint16_t hop_cnt[kWMaxHops];
     uint32_t e_ip[kWMaxEl];
     uint32_t e_op[kWMaxEl];
+    uint8_t e_done[kWMaxEl];    // element complete in the ring (literals after the decode phase, copies once they ran)
     // control words written by thread 0 (or with atomics) between barriers
     uint32_t ip, op;            // stream / output position behind the current chunk
     uint32_t n_hops, n_el;
     uint32_t special;           // a slow-path element follows the chunk
     uint32_t sp_kind, sp_src, sp_len;
-    uint32_t front, any_pending;
     uint32_t err;               // 0 ok, 1.. corrupt (detail), 0x100 cross-fragment reference
 };
 
@@ -154,6 +154,7 @@ k_snappy_frag(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, co
     uint32_t flushed = bias;          // output positions below this are in HBM
     uint32_t valid_from = bias;       // output positions below this are not in the ring (bypassed literal)
     uint32_t tab_ws = 0xffffffffu;    // window the tables describe: [tab_ws, tab_ws + kWWin)
+    uint32_t pf_ws = 0xffffffffu, pf_word = 0;   // stream word of this thread for the window expected next (prefetched)
 
     for (;;) {
         if (sh.err) break;
@@ -164,7 +165,8 @@ k_snappy_frag(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, co
             tab_ws = ip0 & ~3u;
             {
                 const uint32_t pos = tab_ws + 4u * (uint32_t)tid;
-                const uint32_t word = pos < in_end ? __ldg(reinterpret_cast<const uint32_t *>(gin + pos)) : 0u;
+                const uint32_t word = pf_ws == tab_ws ? pf_word
+                                                      : (pos < in_end ? __ldg(reinterpret_cast<const uint32_t *>(gin + pos)) : 0u);
                 uint32_t e[4];
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
@@ -221,6 +223,15 @@ k_snappy_frag(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, co
         __syncthreads();
         if (sh.err) break;
         const uint32_t n_hops = sh.n_hops, n_el = sh.n_el, op_end = sh.op, special = sh.special;
+        {   // the window that follows starts where the walk stopped (unless a slow-path element moves it): fetch its
+            // bytes now, they are needed after this chunk's copies
+            const uint32_t nws = sh.ip & ~3u;
+            if (nws != pf_ws && (nws < tab_ws || nws >= tab_ws + (uint32_t)kWWin)) {
+                const uint32_t pos = nws + 4u * (uint32_t)tid;
+                pf_word = pos < in_end ? __ldg(reinterpret_cast<const uint32_t *>(gin + pos)) : 0u;
+                pf_ws = nws;
+            }
+        }
 
         if (n_el) {
             // ---- 3. expand: eight threads per hop, four elements each
@@ -250,7 +261,7 @@ k_snappy_frag(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, co
             }
             __syncthreads();
             // ---- 4. decode + literals (one thread per element, two passes at most)
-            uint32_t c_d[2], c_a[2], c_len[2];
+            uint32_t c_d[2], c_a[2], c_len[2], c_j[2];
             bool c_pend[2] = {false, false};
 #pragma unroll
             for (int s = 0; s < 2; s++) {
@@ -264,6 +275,7 @@ k_snappy_frag(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, co
                 if (kind == 0) len = t6 + 1;
                 else if (kind == 1) { len = (t6 & 7u) + 4u; a = ((tag >> 5) << 8) | gin[ip + 1]; }
                 else { len = t6 + 1; a = (uint32_t)gin[ip + 1] | ((uint32_t)gin[ip + 2] << 8); }
+                sh.e_done[j] = (uint8_t)(kind == 0);
                 if (used == 0 || ip + used > in_end || d + len > dst_n || (kind != 0 && a == 0)) {
                     atomicMax(&sh.err, 8u);
                     continue;
@@ -276,28 +288,47 @@ k_snappy_frag(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, co
                         atomicMax(&sh.err, (frag_k == 0) ? 8u : 0x100u);
                         continue;
                     }
-                    c_d[s] = d; c_a[s] = a; c_len[s] = len; c_pend[s] = true;
+                    c_d[s] = d; c_a[s] = a; c_len[s] = len; c_j[s] = j; c_pend[s] = true;
                 }
             }
             __syncthreads();
             if (sh.err) break;
-            // ---- 5. back-references in dependency rounds
-            for (;;) {
-                if (tid == 0) sh.front = 0xffffffffu;
-                __syncthreads();
+            // ---- 5. back-references in dependency rounds.  A copy is ready once every element that produces a byte of
+            // its source range is complete: elements of earlier chunks always are; inside the chunk the producing elements
+            // are found by binary search over the (sorted) output positions and their done flags are checked.  The first
+            // pending copy is always ready, so every round makes progress; typical streams need two or three rounds.
+            uint32_t c_lo[2], c_hi[2];
+            const uint32_t chunk_op0 = sh.e_op[0];
 #pragma unroll
-                for (int s = 0; s < 2; s++)
-                    if (c_pend[s]) atomicMin(&sh.front, c_d[s]);
-                __syncthreads();
-                const uint32_t front = sh.front;
-                if (front == 0xffffffffu) break;
+            for (int s = 0; s < 2; s++) {
+                if (!c_pend[s]) continue;
+                const uint32_t sp = c_d[s] - c_a[s];
+                const uint32_t src_end = min(sp + c_len[s], c_d[s]);       // bytes >= d are produced by the copy itself
+                if (src_end <= chunk_op0) { c_lo[s] = 1; c_hi[s] = 0; continue; }      // empty range: nothing to wait for
+                // largest index whose output position is <= q
+                auto find = [&](uint32_t q) {
+                    uint32_t lo = 0, hi = c_j[s];          // the element itself starts at d > q
+                    while (hi - lo > 1) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (sh.e_op[mid] <= q) lo = mid; else hi = mid;
+                    }
+                    return lo;
+                };
+                c_lo[s] = find(max(sp, chunk_op0));
+                c_hi[s] = find(src_end - 1);
+            }
+            for (;;) {
+                bool still = false;
 #pragma unroll
                 for (int s = 0; s < 2; s++) {
                     if (!c_pend[s]) continue;
-                    const uint32_t d = c_d[s], a = c_a[s], len = c_len[s];
-                    const uint32_t sp = d - a;
-                    const uint32_t src_end = min(sp + len, d);       // bytes >= d are produced by the copy itself
-                    if (d != front && src_end > front) continue;
+                    bool ready = true;
+                    for (uint32_t k = c_lo[s]; k <= c_hi[s]; k++)
+                        if (!sh.e_done[k]) { ready = false; break; }
+                    if (!ready) { still = true; continue; }
+                    __threadfence_block();                 // the producers' ring bytes before their done flags
+                    const uint32_t d = c_d[s], len = c_len[s];
+                    const uint32_t sp = d - c_a[s];
                     if (sp >= valid_from && sp + (uint32_t)kWRing >= op_end) {
                         // sequential: an overlapping copy (offset < length) re-reads its own bytes
                         for (uint32_t i = 0; i < len; i++)
@@ -309,9 +340,11 @@ k_snappy_frag(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, co
                             sh.ring[(d + i) & kWRingMask] = q < flushed ? dst[q] : sh.ring[q & kWRingMask];
                         }
                     }
+                    __threadfence_block();
+                    sh.e_done[c_j[s]] = 1;
                     c_pend[s] = false;
                 }
-                __syncthreads();
+                if (!__syncthreads_or(still ? 1 : 0)) break;
             }
             // ---- 6. flush the chunk
             {
