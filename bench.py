@@ -282,9 +282,9 @@ class Workload(object):
 
     @staticmethod
     def batch_rows(batch):
-        first = next(iter(batch.values()))
+        first = batch[next(iter(batch))]
         if isinstance(first, dict):
-            first = next(iter(first.values()))
+            first = first[next(iter(first))]
         return int(first.shape[0])
 
     def d2h_source(self, batch):

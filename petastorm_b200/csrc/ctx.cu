@@ -227,14 +227,8 @@ static int launch_snappy_stage(pst_plan *p, uint8_t *arena, int32_t *status, cud
     }
     if (ev) ck(cudaEventRecord(ev[1], s), "record");
     if (n_frags > 0) {
-        // PST_SNAPPY_PIPELINE=1 selects the three-warp pipeline kernel for the fragments (measurement aid: the wide
-        // window kernel replaced it; the pipeline kernel still serves the serial fallback launch below)
-        static const bool old_kernel = [] { const char *e = getenv("PST_SNAPPY_PIPELINE"); return e && e[0] == '1'; }();
-        if (old_kernel)
-            ck(launch_snappy(arena, pages, frags, n_frags, multi, n_multi, frag_pos, page_flag, status, 0, s),
-               "snappy fragment launch");
-        else
-            ck(launch_snappy_frag(arena, pages, frags, n_frags, frag_pos, page_flag, status, s), "snappy fragment launch");
+        ck(launch_snappy(arena, pages, frags, n_frags, multi, n_multi, frag_pos, page_flag, status, 0, s),
+           "snappy fragment launch");
         nl++;
     }
     if (ev) ck(cudaEventRecord(ev[2], s), "record");
@@ -263,7 +257,6 @@ int pst_ctx_create(int device, int64_t pinned_cache_bytes, int copy_threads, pst
     ck(cudaFree(0), "cuda context init");
     ck(configure_decode_kernels(), "configure kernels");
     ck(configure_copy_kernel(), "configure copy kernel");
-    ck(configure_snappy_wide(), "configure snappy fragment kernel");
     std::unique_ptr<pst_ctx> c(new pst_ctx());
     c->device = device;
     ck(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device), "SM count");

@@ -29,11 +29,6 @@ cudaError_t launch_ba_dict_index(uint8_t *arena, const DevPage *pages, const Dev
 cudaError_t launch_decode_pages(uint8_t *arena, uint8_t *out, const DevCol *cols, const DevPage *pages,
                                 const int32_t *list, int n, int32_t *status, cudaStream_t s);
 
-// ---- kernels_snappy_wide.cu: the fragment decoder (256 threads per 64 KiB fragment, 1 KiB windows of the stream)
-cudaError_t configure_snappy_wide();
-cudaError_t launch_snappy_frag(uint8_t *arena, const DevPage *pages, const SnFrag *frags, int n_frags,
-                               const uint32_t *frag_pos, uint32_t *page_flag, int32_t *status, cudaStream_t s);
-
 // ---- kernels_copy.cu: PLAIN value tiles -> out with the bulk-copy engine (cp.async.bulk + mbarrier)
 cudaError_t configure_copy_kernel();
 cudaError_t launch_copy_tiles(const uint8_t *arena, uint8_t *out, const CopyTile *tiles, int n_tiles, int sm_count,

@@ -285,14 +285,27 @@ class _GpuWorkerBase(WorkerBase):
             return blobs
         vals = col.values.cpu().numpy()
         valid = col.valid.cpu().numpy().astype(bool) if col.valid is not None else np.ones(len(vals), dtype=bool)
-        idx = np.arange(len(vals)) if order is None else order
+        idx = np.arange(len(vals)) if order is None else np.asarray(order)
+        vals, valid = vals[idx], valid[idx]
+        if pt == FIXED_LEN_BYTE_ARRAY and not is_decimal:
+            out = np.empty(len(vals), dtype=object)
+            out[:] = [v.tobytes() for v in vals]
+            out[~valid] = None
+            return list(out)
+        # Decimals are Python objects (one per cell, like upstream); the unscaled integers are assembled with numpy
         if pt == FIXED_LEN_BYTE_ARRAY:
-            if is_decimal:
-                return [self._decimal_from_bytes(vals[i].tobytes(), leaf['scale']) if valid[i] else None for i in idx]
-            return [vals[i].tobytes() if valid[i] else None for i in idx]
-        if is_decimal:  # INT32 / INT64 decimals
-            return [Decimal(int(vals[i])).scaleb(-leaf['scale']) if valid[i] else None for i in idx]
-        raise ValueError('no host form for physical type {}'.format(pt))
+            width = vals.shape[1] if vals.ndim == 2 else 0
+            if 0 < width <= 8:
+                be = np.zeros((len(vals), 8), dtype=np.uint8)
+                be[:, 8 - width:] = vals
+                be[:, :8 - width] = np.where(vals[:, :1] & 0x80, 0xff, 0)       # sign extension
+                ints = be.view('>i8').ravel().tolist()
+            else:
+                ints = [int.from_bytes(v.tobytes(), 'big', signed=True) for v in vals]
+        else:               # INT32 / INT64 decimals
+            ints = vals.tolist()
+        scale = leaf['scale']
+        return [Decimal(i).scaleb(-scale) if ok else None for i, ok in zip(ints, valid.tolist())]
 
     @staticmethod
     def _datetime_array(col, leaf, order, null_count):
@@ -446,11 +459,11 @@ class GpuArrowWorker(_GpuWorkerBase):
         if nulls:
             pt = col.physical_type
             if pt == BOOLEAN:
-                # pandas yields an object column of True/False/None
-                vals = t.cpu().numpy()
+                # pandas yields an object column of True/False/None (no tensor form); built with numpy, not per row
+                vals = t.cpu().numpy().astype(bool)
                 valid = col.valid.cpu().numpy().astype(bool)
-                arr = np.empty(len(vals), dtype=object)
-                arr[:] = [bool(v) if ok else None for v, ok in zip(vals, valid)]
+                arr = vals.astype(object)
+                arr[~valid] = None
                 return arr if order is None else arr[order]
             bits, signed = integer_logical_type(leaf) if pt in (INT32, INT64) else (0, True)
             t = device_ops.nulls_to_nan(col.values, col.valid, pt, bits, not signed)

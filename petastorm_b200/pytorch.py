@@ -177,12 +177,58 @@ class _DeviceGroups(object):
                         'fields {}'.format([k for k, v in cols.items() if not _is_tensor_column(v)]))
 
 
+class _NGramBatch(dict):
+    """``{offset: {field: tensor[batch, ...]}}`` over the ``[batch, L, ...]`` field tensors of a batch of NGram windows.
+    The per-offset dicts are views (no copies) and are only built when an offset is looked at: an NGram of length 16
+    over 13 fields would otherwise cost 208 tensor objects per batch whether the training loop reads them or not."""
+
+    def __init__(self, fields, timesteps):
+        super(_NGramBatch, self).__init__()
+        self._fields = fields
+        self._timesteps = timesteps
+        self._base = min(timesteps)
+
+    def __missing__(self, offset):
+        if offset not in self._timesteps:
+            raise KeyError(offset)
+        item = {name: self._fields[name][:, offset - self._base] for name in self._timesteps[offset]
+                if name in self._fields}
+        dict.__setitem__(self, offset, item)
+        return item
+
+    def __contains__(self, offset):
+        return offset in self._timesteps
+
+    def __iter__(self):
+        return iter(self._timesteps)
+
+    def __len__(self):
+        return len(self._timesteps)
+
+    def keys(self):
+        return self._timesteps.keys()
+
+    def values(self):
+        return [self[k] for k in self._timesteps]
+
+    def items(self):
+        return [(k, self[k]) for k in self._timesteps]
+
+    def get(self, offset, default=None):
+        return self[offset] if offset in self._timesteps else default
+
+    def __repr__(self):
+        return repr(dict(self.items()))
+
+    @property
+    def windows(self):
+        """``{field: tensor[batch, L, ...]}`` - the whole windows, one tensor per field."""
+        return self._fields
+
+
 def _nest_ngram_batch(keys, values, timesteps):
-    """``[W, L, ...]`` field tensors of a batch -> ``{offset: {field: tensor[W, ...]}}`` (views, no copies)."""
-    by_name = dict(zip(keys, values))
-    base = min(timesteps)
-    return {t: {name: by_name[name][:, t - base] for name in names if name in by_name}
-            for t, names in timesteps.items()}
+    """``[W, L, ...]`` field tensors of a batch -> ``{offset: {field: tensor[W, ...]}}`` (lazy views, no copies)."""
+    return _NGramBatch(dict(zip(keys, values)), timesteps)
 
 
 class DataLoader(LoaderBase):
