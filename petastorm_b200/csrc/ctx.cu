@@ -262,8 +262,11 @@ int pst_ctx_create(int device, int64_t pinned_cache_bytes, int copy_threads, pst
     ck(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device), "SM count");
     c->cache_budget = pinned_cache_bytes;
     if (copy_threads < 0) {
+        // staging copies (page cache -> pinned) of the cold path: 12 threads moved 290 MB in 15 ms (19 GB/s, r2g); up to
+        // 16 by default, PST_COPY_THREADS overrides (8 ranks of a box share the host cores)
         unsigned hc = std::thread::hardware_concurrency();
-        copy_threads = hc > 2 ? (int)std::min<unsigned>(hc - 1, 12) : 0;
+        copy_threads = hc > 2 ? (int)std::min<unsigned>(hc - 1, 16) : 0;
+        if (const char *e = getenv("PST_COPY_THREADS")) copy_threads = std::max(0, atoi(e));
     }
     c->local_cpus = local_cpus_of_device(device);
     if (copy_threads > 0) c->pool.reset(new CopyPool(copy_threads, c->local_cpus));

@@ -71,6 +71,7 @@ struct JpegState {
     int batch = 0;
     int backend = -1;
     bool tried = false;
+    cudaEvent_t last = nullptr;    // end of the previous batch decoded with this state (its scratch buffers are reused)
     std::mutex mu;
 };
 
@@ -78,9 +79,11 @@ JpegState &jstate() {
     static JpegState s;
     return s;
 }
-// a second handle whose batched decode reads the bitstreams from DEVICE memory (no blob D2H)
-JpegState &jstate_device() {
-    static JpegState s;
+// handles whose batched decode reads the bitstreams from DEVICE memory (no blob D2H); two of them, so that the
+// resolver threads of a pool can have two batches in nvJPEG at the same time (its host-side work per batch is serial)
+constexpr int kDeviceStates = 2;
+JpegState *device_states() {
+    static JpegState s[kDeviceStates];
     return s;
 }
 
@@ -105,12 +108,9 @@ int pst_jpeg_available(void) { return api().ok ? 1 : 0; }
 
 int pst_jpeg_backend(void) { return jstate().backend; }
 
-int pst_jpeg_device_backend(void) {
-    // creates the device-bitstream handle on first use: the hardware JPEG engines first, then GPU-assisted Huffman
-    NvjpegApi &a = api();
-    if (!a.ok) return -1;
-    JpegState &js = jstate_device();
-    std::lock_guard<std::mutex> g(js.mu);
+// creates the device-bitstream handle of one state on first use: the hardware JPEG engines first, then GPU-assisted
+// Huffman; returns its nvjpegBackend_t or -1 (caller holds js.mu)
+static int ensure_device_state(NvjpegApi &a, JpegState &js) {
     if (!js.tried) {
         js.tried = true;
         const char *skip_hw = getenv("PST_JPEG_NO_HW");
@@ -130,6 +130,14 @@ int pst_jpeg_device_backend(void) {
     return js.backend;
 }
 
+int pst_jpeg_device_backend(void) {
+    NvjpegApi &a = api();
+    if (!a.ok) return -1;
+    JpegState &js = device_states()[0];
+    std::lock_guard<std::mutex> g(js.mu);
+    return ensure_device_state(a, js);
+}
+
 int pst_jpeg_batch_device(pst_ctx *c, uint64_t base, const int64_t *host_offs, const int32_t *host_lens, int64_t n,
                           int height, int width, uint64_t dst, uint64_t stream) {
     (void)c;
@@ -137,10 +145,24 @@ int pst_jpeg_batch_device(pst_ctx *c, uint64_t base, const int64_t *host_offs, c
         NvjpegApi &a = api();
         if (!a.ok) throw std::runtime_error("nvJPEG unavailable: " + a.why);
         if (n <= 0) return 0;
-        if (pst_jpeg_device_backend() < 0)
+        // a free state, else wait for the first one
+        JpegState *states = device_states();
+        std::unique_lock<std::mutex> g;
+        JpegState *jsp = nullptr;
+        for (int k = 0; k < kDeviceStates && !jsp; k++) {
+            std::unique_lock<std::mutex> t(states[k].mu, std::try_to_lock);
+            if (t.owns_lock()) {
+                g = std::move(t);
+                jsp = &states[k];
+            }
+        }
+        if (!jsp) {
+            g = std::unique_lock<std::mutex>(states[0].mu);
+            jsp = &states[0];
+        }
+        JpegState &js = *jsp;
+        if (ensure_device_state(a, js) < 0)
             throw std::runtime_error("this nvJPEG has no backend that decodes device-resident bitstreams");
-        JpegState &js = jstate_device();
-        std::lock_guard<std::mutex> g(js.mu);
         if (js.batch != (int)n) {
             nvjpegStatus_t st = a.DecodeBatchedInitialize(js.handle, js.state, (int)n, 1, NVJPEG_OUTPUT_RGBI);
             if (st != NVJPEG_STATUS_SUCCESS)
@@ -155,7 +177,11 @@ int pst_jpeg_batch_device(pst_ctx *c, uint64_t base, const int64_t *host_offs, c
         }
         std::vector<nvjpegImage_t> outs((size_t)n);
         fill_outputs(outs, dst, n, height, width);
+        // batches of different row-groups run on different streams: order them on the state's own buffers
+        if (!js.last) cudaEventCreateWithFlags(&js.last, cudaEventDisableTiming);
+        else cudaStreamWaitEvent((cudaStream_t)stream, js.last, 0);
         nvjpegStatus_t st = a.DecodeBatched(js.handle, js.state, ptrs.data(), lens.data(), outs.data(), (cudaStream_t)stream);
+        if (js.last) cudaEventRecord(js.last, (cudaStream_t)stream);
         if (st != NVJPEG_STATUS_SUCCESS) {
             js.batch = 0;
             throw std::runtime_error("nvjpegDecodeBatched (device bitstreams, backend " + std::to_string(js.backend) +

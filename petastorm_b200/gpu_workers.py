@@ -112,7 +112,7 @@ class _GpuWorkerBase(WorkerBase):
         self._options = args[12] if len(args) > 12 and args[12] is not None else WorkerOptions()
         self._rng = np.random.default_rng(self._random_seed)
         self._decoder = None
-        self._post_stream = None
+        self._post_streams = {}
         self.rows_decoded = 0
         self.payload_bytes = 0
         self.t_issue = self.t_wait = self.t_build = 0.0   # host seconds: issuing device work / waiting / building columns
@@ -167,9 +167,20 @@ class _GpuWorkerBase(WorkerBase):
         is finalised, the issuing thread has already queued later row-groups (H2D + ~15 ms of decode) on that stream
         and anything appended there - in particular the `done` event the consumer waits for - would sit behind them.
         ``decoded.wait()`` (``_build_columns``) orders this stream after the row-group's own decode."""
-        if self._post_stream is None:
-            self._post_stream = torch.cuda.Stream(self._get_decoder().device)
-        return self._post_stream
+        return self._thread_post_stream()
+
+    def _thread_post_stream(self):
+        """One post-processing stream per host thread that resolves row-groups (consumer, resolver threads): the
+        blocking host reads of one resolution then never wait for another one's kernels."""
+        import threading
+        streams = self._post_streams
+        ident = threading.get_ident()
+        stream = streams.get(ident)
+        if stream is None:
+            device = self._get_decoder().device
+            torch.cuda.set_device(device)          # resolver threads start on device 0
+            stream = streams[ident] = torch.cuda.Stream(device)
+        return stream
 
     # ---- row selection ------------------------------------------------------------------------------------------
     def _row_order(self, num_rows, shuffle_row_drop_partition, ngram_length=0):
@@ -590,14 +601,26 @@ class PendingRowGroup(object):
         self._finalize = finalize
         self._result = None
         self._done = False
+        self._future = None
         self.num_rows = num_rows
 
-    def resolve(self):
+    def resolve_ahead(self, executor):
+        """Start the resolution on a resolver thread of the pool (codec launches and their host-side waits then
+        overlap the consumer's work on the previous row-group); ``resolve`` waits for it."""
+        if self._future is None and not self._done:
+            self._future = executor.submit(self._run)
+
+    def _run(self):
         if not self._done:
             self._result = self._finalize()
             self._finalize = None
             self._done = True
         return self._result
+
+    def resolve(self):
+        if self._future is not None:
+            return self._future.result()
+        return self._run()
 
 
 def _record_on_current_stream(columns):
@@ -1245,11 +1268,9 @@ class GpuPyDictWorker(_GpuWorkerBase):
         if isinstance(ts, ScalarColumn):
             ts = ts.tensor
         device = self._get_decoder().device
-        if self._post_stream is None:
-            self._post_stream = torch.cuda.Stream(device)
         ts_list = [_npify(v) for v in ts] if not isinstance(ts, torch.Tensor) else None
         starts_dev = None
-        with torch.cuda.stream(self._post_stream):
+        with torch.cuda.stream(self._thread_post_stream()):
             if ts_list is not None and len(ts_list) and isinstance(ts_list[0], (np.integer, int)) and \
                     all(v is not None for v in ts_list):
                 ts_dev = torch.tensor(np.asarray(ts_list, dtype=np.int64), device=device)

@@ -62,11 +62,12 @@ def _resolve_device(device):
     return int(device)
 
 
-def _make_pool(reader_pool_type, workers_count, results_queue_size, device):
+def _make_pool(reader_pool_type, workers_count, results_queue_size, device, resolvers=0):
     if reader_pool_type in ('thread', 'process'):
         # row-groups in flight: one being consumed, one or two decoding (~3 ms), one copying (~5 ms), one queued behind
         # it so that the PCIe copy engine never idles
-        pool = GpuPool(workers_count=1, results_queue_size=min(max(int(results_queue_size), 1), 6), device=device)
+        pool = GpuPool(workers_count=1, results_queue_size=min(max(int(results_queue_size), 1), 6), device=device,
+                       resolvers=resolvers)
         pool.max_in_flight = int(os.environ.get('PST_MAX_IN_FLIGHT', '6'))
         return pool
     if reader_pool_type == 'dummy':
@@ -100,15 +101,22 @@ def make_reader(dataset_url,
     filesystem, dataset_path = get_filesystem_and_path_or_paths(dataset_url_or_urls, hdfs_driver,
                                                                 storage_options=storage_options, filesystem=filesystem)
     cache = _make_cache(cache_type, cache_location, cache_size_limit, cache_row_size_estimate, cache_extra_settings)
+    resolvers = 0
     try:
-        dataset_metadata.get_schema(dataset_metadata.ParquetDataset(dataset_path))
+        stored = dataset_metadata.get_schema(dataset_metadata.ParquetDataset(dataset_path))
+        # nvJPEG's batched decode has milliseconds of host-side work per row-group: resolve those row-groups ahead of the
+        # consumer on two threads (see GpuPool)
+        from petastorm_b200.codecs import CompressedImageCodec
+        if any(isinstance(f.codec, CompressedImageCodec) and f.codec.image_codec in ('jpeg', 'jpg')
+               for f in stored.fields.values()):
+            resolvers = 2
     except PetastormMetadataError:
         warnings.warn('Currently make_reader supports reading only Petastorm datasets. '
                       'To read from a non-Petastorm Parquet store use make_batch_reader')
     if reader_pool_type == 'process' and pyarrow_serialize:
         warnings.warn('pyarrow_serializer was deprecated and will be removed in future versions. '
                       'The argument no longer has any effect.')
-    reader_pool = _make_pool(reader_pool_type, workers_count, results_queue_size, device)
+    reader_pool = _make_pool(reader_pool_type, workers_count, results_queue_size, device, resolvers)
     try:
         return Reader(filesystem, dataset_path,
                       worker_class=GpuPyDictWorker, is_batched_reader=False,

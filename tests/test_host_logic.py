@@ -776,3 +776,25 @@ def test_local_disk_cache_validation_and_eviction(tmp_path):
         gpu_workers.to_host_payload, gpu_workers.from_host_payload = real_to, real_from
     cache.cleanup()
     assert not os.path.exists(str(tmp_path / 'c2'))
+
+
+def test_planner_indexes_blob_pages_on_the_host(tmp_path):
+    """Blob columns (1 MiB tensors, jpeg images) are practically incompressible and pyarrow writes a whole column chunk of
+    large values as ONE page: the planner walks the few Snappy tags of such literal-dominated pages itself
+    (num_host_indexed_pages) instead of leaving a multi-megabyte page to the serial walk of k_snappy_index, and indexes the
+    BYTE_ARRAY dictionary of pages the device sees uncompressed."""
+    import glob
+    from petastorm_b200 import native
+    url = datasets.build('tensor_c4', str(tmp_path / 'c4'), 8, row_group_rows=8)
+    f = native.ParquetFile(glob.glob(url[7:] + '/*.parquet')[0])
+    info = native.Plan(f, 0, list(range(f.num_columns))).info
+    assert info.num_snappy_fragments >= 8 * 16          # the tensor page still decompresses on the device, in parallel
+    assert info.num_index_pages == 0 and info.num_host_indexed_pages >= 1
+    # a compressible multi-fragment page is left to the device index
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    path = str(tmp_path / 'narrow.parquet')
+    pq.write_table(pa.table({'narrow': np.random.default_rng(0).integers(0, 2 ** 20, 300000, dtype=np.int64)}), path,
+                   compression='snappy', use_dictionary=False, data_page_size=1 << 20)
+    info = native.Plan(native.ParquetFile(path), 0, [0]).info
+    assert info.num_index_pages >= 2 and info.num_host_indexed_pages == 0
