@@ -101,8 +101,10 @@ def hbm_peak():
 
 # ncu --set full DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernels, from the
 # committed capture of this round
-NCU_DRAM_SOURCE = 'profiles/r2a_copy_tiles_unwrapped_pages.txt (ncu --set full, one launch on a C2 row-group)'
-NCU_DRAM_BYTES_PER_LAUNCH = {'k_snappy_pages': 120353024, 'k_copy_tiles': 292158208, 'k_decode_pages': 177854464}
+NCU_DRAM_SOURCE = ('profiles/r2final_c2_decode_kernels.txt (ncu --set full, one launch on a C2 row-group; k_snappy_index '
+                   'from profiles/r2e_wide_fragment_kernel_v1.txt)')
+NCU_DRAM_BYTES_PER_LAUNCH = {'k_snappy_index': 77995264, 'k_snappy_pages': 120274432, 'k_copy_tiles': 293706752,
+                             'k_decode_pages': 181324288}
 
 
 def plan_algorithmic_bytes(plan):
@@ -263,6 +265,7 @@ class Workload(object):
     key = None
     rows_per_group = 0
     decoded_row_bytes = 0        # D per delivered sample
+    value_steps_min = 0          # row-groups of the HBM-resident leg: at least this many, for a timed region of >= 0.25 s
     batch = 1
     delivered_fraction = 1.0     # delivered samples / stored rows (predicate, NGram window yield)
 
@@ -303,6 +306,7 @@ def _specs(kind):
 
 class C1(Workload):
     key, rows_per_group, batch = 'c1', 256, 64
+    value_steps_min = 128
     decoded_row_bytes = 4 + 128 * 256 * 3 + 4 * 128 * 30 * 3
 
     def describe(self, n_groups, world):
@@ -329,6 +333,7 @@ class C1(Workload):
 
 class C3(Workload):
     key, rows_per_group, batch = 'c3', 1024, 256
+    value_steps_min = 48
     decoded_row_bytes = 224 * 224 * 3 + 4
 
     def describe(self, n_groups, world):
@@ -356,6 +361,7 @@ class C3(Workload):
 
 class C4(Workload):
     key, rows_per_group, batch = 'c4', 128, 32
+    value_steps_min = 192
     decoded_row_bytes = 32 * 128 * 128 * 2 + 4
     delivered_fraction = 0.5
     MEAN, STD = 0.25, 1.5
@@ -392,6 +398,7 @@ class C4(Workload):
 
 class C5(Workload):
     key, rows_per_group, batch = 'c5', 131072, 1024
+    value_steps_min = 16
     LENGTH, CAPACITY = 16, 100000
     decoded_row_bytes = 16 * (12 * 4 + 8)
     delivered_fraction = (1000 - 15) / 1000.0
@@ -890,10 +897,11 @@ def run_rows(args, w, rank, local_rank, world, cores):
                 'device_batched': getattr(loader, 'device_batched', None)}
 
     # ---- (1) value: raw bytes resident in HBM ------------------------------------------------------------------------
-    r = run_leg(args.steps, args.warmup, resident=True)
+    value_steps = max(args.steps, w.value_steps_min)
+    r = run_leg(value_steps, args.warmup, resident=True)
     value = r['rows_all'] / (r['dev_ms'] / 1e3)
-    gpu_launches = r['launches']
-    value_info = {'hbm_cache_hits': r['hbm_hits'], 'h2d_bytes_in_region': r['h2d'],
+    gpu_launches = r['launches'] * args.steps // value_steps
+    value_info = {'steps_timed': value_steps, 'hbm_cache_hits': r['hbm_hits'], 'h2d_bytes_in_region': r['h2d'],
                   'device_batched_loader': r['device_batched'], 'region_ms': r['dev_ms']}
 
     # ---- (2) e2e from host buffers -------------------------------------------------------------------------------------

@@ -19,6 +19,17 @@ __device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t *p) {
     return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
 }
 
+// Little-endian 32-bit value at any address as two aligned word loads + a funnel shift: ONE memory latency on a serial
+// chain (length prefixes of BYTE_ARRAY values) instead of four byte loads.  Reads the aligned words that contain
+// [p, p+4): up to 3 bytes in front of p and behind p+3 (the planner leaves that slack around every page image).
+__device__ __forceinline__ uint32_t ld_u32_chain(const uint8_t *p) {
+    const uint32_t mis = (uint32_t)((uintptr_t)p & 3);
+    const uint32_t *a = reinterpret_cast<const uint32_t *>(p - mis);
+    const uint32_t w0 = a[0];
+    const uint32_t w1 = mis ? a[1] : 0u;
+    return __funnelshift_r(w0, w1, mis * 8);
+}
+
 // 16 bytes starting `m` bytes into the 32-byte window {a, b}
 __device__ __forceinline__ uint4 extract16(uint4 a, uint4 b, uint32_t m) {
     uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};

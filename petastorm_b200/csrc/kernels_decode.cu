@@ -924,7 +924,7 @@ __global__ void k_ba_dict_index(uint8_t *__restrict__ arena, const DevPage *__re
     int64_t pos = 0;
     for (int i = 0; i < col.dict_count; i++) {
         if (pos + 4 > pg.uncomp_size) { report_error(status, DE_BYTE_ARRAY_CORRUPT, pi, i); return; }
-        uint32_t len = ld_u32_unaligned(img + pos);
+        uint32_t len = ld_u32_chain(img + pos);
         pos += 4;
         if (pos + len > (int64_t)pg.uncomp_size) { report_error(status, DE_BYTE_ARRAY_CORRUPT, pi, i); return; }
         idx[i].off = pg.img_off + pos;
@@ -1307,7 +1307,7 @@ k_decode_pages(uint8_t *__restrict__ arena, uint8_t *__restrict__ out, const Dev
                 const int64_t lim = sh.val_end - val_ptr;
                 for (uint32_t r = 0; r < tile_valid; r++) {
                     if (pos + 4 > lim) { sh.fail = 1; break; }
-                    uint32_t len = ld_u32_unaligned(val_ptr + pos);
+                    uint32_t len = ld_u32_chain(val_ptr + pos);
                     pos += 4;
                     if (pos + (int64_t)len > lim) { sh.fail = 1; break; }
                     sh.s_ba_off[r] = (val_ptr - arena) + pos;
