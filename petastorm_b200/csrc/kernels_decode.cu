@@ -82,7 +82,9 @@ struct SnBatch {
 static_assert(sizeof(SnBatch) == 96, "SnBatch layout");
 constexpr uint32_t kHdrOff = kHops * 8;
 // successor tables of the parser (see warp P)
-constexpr int kTabW = 1024;           // input positions covered by one table build (static shared memory <= 48 KiB)
+constexpr int kTabW = 256;            // input positions covered by one table build.  (1024 in the first version: with 256 and
+                                      // the tag -> length lookup done in registers the CTA needs 27.2 KiB instead of 31.3 KiB of
+                                      // shared memory: 8 fragments per SM instead of 7)
 constexpr int kTabPad = 64;           // zero entries behind the window: an element is at most 61 bytes long
 
 
@@ -176,6 +178,14 @@ struct SnExec {                 // warp A -> warp B: the back-references of one 
 static_assert(sizeof(SnExec) == 416, "SnExec layout");
 constexpr uint32_t kExecHdr = kBatchOps * 12;
 
+// bytes an element occupies in the stream as a function of its tag; 0 = slow path (copy with a 4-byte offset, literal
+// with a length suffix)
+__device__ __forceinline__ uint32_t snappy_step_of(uint32_t tag) {
+    const uint32_t kind = tag & 3u, t6 = tag >> 2;
+    const uint32_t lit = t6 < 60u ? t6 + 2u : 0u;
+    return kind == 0u ? lit : (kind == 3u ? 0u : kind + 1u);
+}
+
 __global__ void __launch_bounds__(kSnappyThreads)
 k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, const SnFrag *__restrict__ frags,
                int n_frags, const int32_t *__restrict__ multi_list, int n_multi, const uint32_t *__restrict__ frag_pos,
@@ -186,7 +196,6 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
     __shared__ __align__(16) SnExec execs[2];
     __shared__ __align__(16) uint32_t quad_tab[kTabW + kTabPad];
     __shared__ __align__(16) uint8_t step_tab[kTabW + kTabPad];
-    __shared__ __align__(16) uint8_t step_lut[256];
     __shared__ volatile uint32_t abort_flag;
     uint8_t *const ring = smem_all;
     uint8_t *const stage = smem_all + kRing + 16;
@@ -218,12 +227,6 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
     uint32_t src_n = (uint32_t)pg.comp_size;
     uint32_t dst_n = (uint32_t)pg.uncomp_size;
     if (threadIdx.x == 0) abort_flag = 0;
-    // bytes an element occupies in the stream as a function of its tag; 0 = slow path (copy with 4-byte offset,
-    // literal with a length suffix)
-    for (int t = threadIdx.x; t < 256; t += kSnappyThreads) {
-        const int kind = t & 3, t6 = t >> 2;
-        step_lut[t] = (uint8_t)(kind == 0 ? (t6 < 60 ? t6 + 2 : 0) : kind == 1 ? 2 : kind == 2 ? 3 : 0);
-    }
     for (int t = threadIdx.x; t < kTabPad; t += kSnappyThreads) {
         step_tab[kTabW + t] = 0;
         quad_tab[kTabW + t] = 0;
@@ -266,7 +269,6 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
         const uint32_t stage_s = shared_addr(stage);
         const uint32_t batches_s = shared_addr(&batches[0]);
         const uint32_t quad_s = shared_addr(&quad_tab[0]), step_s = shared_addr(&step_tab[0]);
-        const uint32_t lut_s = shared_addr(&step_lut[0]);
         uint32_t tab_w0 = 0, tab_end = 0;             // input window [tab_w0, tab_end) the tables describe
         if (has_preamble) {   // varint uncompressed length (a handful of bytes, read straight from global)
             uint64_t ulen = 0;
@@ -324,7 +326,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
             bool covered = !stop && ip < in_end && ip >= tab_w0 && ip < tab_end;
             if (!stop && ip < in_end && !covered) {
                 const uint32_t tag0 = lds_u8(stage_s + (ip & kStageMask));
-                if (lds_u8(lut_s + tag0) != 0) {   // a window that starts with a slow-path element is not worth a build
+                if (snappy_step_of(tag0) != 0) {   // a window that starts with a slow-path element is not worth a build
                     const uint32_t w0 = ip & ~3u;
                     // (volatile asm accessors execute in program order: batch the loads, then use them)
                     {
@@ -337,7 +339,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                             uint32_t e[8];
 #pragma unroll
                             for (int q = 0; q < 8; q++)
-                                e[q] = lds_u8(lut_s + ((word[h + (q >> 2)] >> (8 * (q & 3))) & 0xffu));
+                                e[q] = snappy_step_of((word[h + (q >> 2)] >> (8 * (q & 3))) & 0xffu);
 #pragma unroll
                             for (int q = 0; q < 2; q++) {
                                 const uint32_t wi = (uint32_t)lane + 32u * (uint32_t)(h + q);
