@@ -808,7 +808,9 @@ def run_c2(args, rank, local_rank, world, cores):
 # C1 / C3 / C4 / C5: make_reader + loader
 # =====================================================================================================================
 def run_rows(args, w, rank, local_rank, world, cores):
-    n_groups = max(args.row_groups, 2 * world)
+    # four distinct row-groups per rank: with two, consecutive decodes of the HBM-resident leg wait for each other (the
+    # same cached arena is decoded again two steps later) and the 8-GPU `value` of C3 came out below its `e2e`
+    n_groups = max(args.row_groups, 4 * world)
     rows_pg = w.rows_per_group
     delivered_pg = rows_pg * w.delivered_fraction
     config = {'workload': w.describe(n_groups, world), 'rows_per_row_group': rows_pg,
