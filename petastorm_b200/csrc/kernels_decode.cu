@@ -82,9 +82,7 @@ struct SnBatch {
 static_assert(sizeof(SnBatch) == 96, "SnBatch layout");
 constexpr uint32_t kHdrOff = kHops * 8;
 // successor tables of the parser (see warp P)
-constexpr int kTabW = 256;            // input positions covered by one table build.  (1024 in the first version: with 256 and
-                                      // the tag -> length lookup done in registers the CTA needs 27.2 KiB instead of 31.3 KiB of
-                                      // shared memory: 8 fragments per SM instead of 7)
+constexpr int kTabW = 1024;           // input positions covered by one table build (static shared memory <= 48 KiB)
 constexpr int kTabPad = 64;           // zero entries behind the window: an element is at most 61 bytes long
 
 
@@ -155,6 +153,55 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
+template <int K>
+__device__ __forceinline__ uint32_t lds_u8_off(uint32_t addr) {      // immediate offsets: no address arithmetic per byte
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1+%2];\n" : "=r"(v) : "r"(addr), "n"(K));
+    return v;
+}
+template <int K>
+__device__ __forceinline__ void sts_u8_off(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u8 [%0+%2], %1;\n" ::"r"(addr), "r"(v), "n"(K) : "memory");
+}
+// `len` >= 1 bytes from position sp of one power-of-two shared-memory buffer to position d of another (or the same), in
+// stream order.  The decoder's time goes with the number of instructions its three warps execute per batch, and the
+// byte moves were a quarter of them (11 instructions per byte with masked addresses, r2final source profile): runs that
+// do not wrap - all but a few per fragment - use two running addresses and immediate offsets, 3 instructions per byte.
+// `grouped`: the source does not overlap the last four bytes written (literals; back-references with distance >= 4), so
+// four loads may be issued before their stores.
+__device__ __forceinline__ void smem_bytes(uint32_t src_s, uint32_t smask, uint32_t sp, uint32_t dst_s, uint32_t dmask,
+                                           uint32_t d, uint32_t len, bool grouped) {
+    const uint32_t so = sp & smask, dof = d & dmask;
+#ifdef PST_SNAPPY_NOGROUP
+    grouped = false;
+#endif
+#ifndef PST_SNAPPY_LEAN
+    if (false)
+#else
+    if (so + len <= smask + 1u && dof + len <= dmask + 1u)
+#endif
+    {
+        uint32_t sa = src_s + so, da = dst_s + dof;
+        uint32_t n4 = len >> 2;
+        if (grouped) {
+            for (; n4; n4--, sa += 4, da += 4) {
+                const uint32_t v0 = lds_u8_off<0>(sa), v1 = lds_u8_off<1>(sa), v2 = lds_u8_off<2>(sa), v3 = lds_u8_off<3>(sa);
+                sts_u8_off<0>(da, v0); sts_u8_off<1>(da, v1); sts_u8_off<2>(da, v2); sts_u8_off<3>(da, v3);
+            }
+        } else {
+            for (; n4; n4--, sa += 4, da += 4) {
+                sts_u8_off<0>(da, lds_u8_off<0>(sa)); sts_u8_off<1>(da, lds_u8_off<1>(sa));
+                sts_u8_off<2>(da, lds_u8_off<2>(sa)); sts_u8_off<3>(da, lds_u8_off<3>(sa));
+            }
+        }
+        const uint32_t r = len & 3u;
+        if (r > 0) sts_u8_off<0>(da, lds_u8_off<0>(sa));
+        if (r > 1) sts_u8_off<1>(da, lds_u8_off<1>(sa));
+        if (r > 2) sts_u8_off<2>(da, lds_u8_off<2>(sa));
+        return;
+    }
+    for (uint32_t i = 0; i < len; i++) sts_u8(dst_s + ((d + i) & dmask), lds_u8(src_s + ((sp + i) & smask)));
+}
 // Hand-over between the stages is a RENDEZVOUS on one named barrier per pair of warps: when P and A meet, P has finished
 // writing batch b+1 and A has finished reading batch b (the slots are double-buffered), then both move on.  Two named
 // barriers per CTA (plus barrier 0) instead of eight keep the barrier file of the SM (64) from limiting residency.
@@ -178,14 +225,6 @@ struct SnExec {                 // warp A -> warp B: the back-references of one 
 static_assert(sizeof(SnExec) == 416, "SnExec layout");
 constexpr uint32_t kExecHdr = kBatchOps * 12;
 
-// bytes an element occupies in the stream as a function of its tag; 0 = slow path (copy with a 4-byte offset, literal
-// with a length suffix)
-__device__ __forceinline__ uint32_t snappy_step_of(uint32_t tag) {
-    const uint32_t kind = tag & 3u, t6 = tag >> 2;
-    const uint32_t lit = t6 < 60u ? t6 + 2u : 0u;
-    return kind == 0u ? lit : (kind == 3u ? 0u : kind + 1u);
-}
-
 __global__ void __launch_bounds__(kSnappyThreads)
 k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, const SnFrag *__restrict__ frags,
                int n_frags, const int32_t *__restrict__ multi_list, int n_multi, const uint32_t *__restrict__ frag_pos,
@@ -196,6 +235,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
     __shared__ __align__(16) SnExec execs[2];
     __shared__ __align__(16) uint32_t quad_tab[kTabW + kTabPad];
     __shared__ __align__(16) uint8_t step_tab[kTabW + kTabPad];
+    __shared__ __align__(16) uint8_t step_lut[256];
     __shared__ volatile uint32_t abort_flag;
     uint8_t *const ring = smem_all;
     uint8_t *const stage = smem_all + kRing + 16;
@@ -227,6 +267,12 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
     uint32_t src_n = (uint32_t)pg.comp_size;
     uint32_t dst_n = (uint32_t)pg.uncomp_size;
     if (threadIdx.x == 0) abort_flag = 0;
+    // bytes an element occupies in the stream as a function of its tag; 0 = slow path (copy with 4-byte offset,
+    // literal with a length suffix)
+    for (int t = threadIdx.x; t < 256; t += kSnappyThreads) {
+        const int kind = t & 3, t6 = t >> 2;
+        step_lut[t] = (uint8_t)(kind == 0 ? (t6 < 60 ? t6 + 2 : 0) : kind == 1 ? 2 : kind == 2 ? 3 : 0);
+    }
     for (int t = threadIdx.x; t < kTabPad; t += kSnappyThreads) {
         step_tab[kTabW + t] = 0;
         quad_tab[kTabW + t] = 0;
@@ -269,6 +315,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
         const uint32_t stage_s = shared_addr(stage);
         const uint32_t batches_s = shared_addr(&batches[0]);
         const uint32_t quad_s = shared_addr(&quad_tab[0]), step_s = shared_addr(&step_tab[0]);
+        const uint32_t lut_s = shared_addr(&step_lut[0]);
         uint32_t tab_w0 = 0, tab_end = 0;             // input window [tab_w0, tab_end) the tables describe
         if (has_preamble) {   // varint uncompressed length (a handful of bytes, read straight from global)
             uint64_t ulen = 0;
@@ -326,7 +373,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
             bool covered = !stop && ip < in_end && ip >= tab_w0 && ip < tab_end;
             if (!stop && ip < in_end && !covered) {
                 const uint32_t tag0 = lds_u8(stage_s + (ip & kStageMask));
-                if (snappy_step_of(tag0) != 0) {   // a window that starts with a slow-path element is not worth a build
+                if (lds_u8(lut_s + tag0) != 0) {   // a window that starts with a slow-path element is not worth a build
                     const uint32_t w0 = ip & ~3u;
                     // (volatile asm accessors execute in program order: batch the loads, then use them)
                     {
@@ -339,7 +386,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                             uint32_t e[8];
 #pragma unroll
                             for (int q = 0; q < 8; q++)
-                                e[q] = snappy_step_of((word[h + (q >> 2)] >> (8 * (q & 3))) & 0xffu);
+                                e[q] = lds_u8(lut_s + ((word[h + (q >> 2)] >> (8 * (q & 3))) & 0xffu));
 #pragma unroll
                             for (int q = 0; q < 2; q++) {
                                 const uint32_t wi = (uint32_t)lane + 32u * (uint32_t)(h + q);
@@ -455,6 +502,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
         const uint32_t ring_s = shared_addr(ring), stage_s = shared_addr(stage), batches_s = shared_addr(&batches[0]);
         const uint32_t execs_s = shared_addr(&execs[0]);
         uint32_t dst0 = bias;         // output position of the next batch
+        uint32_t valid_from = bias;   // output positions below this never were in the ring (bypassed literal); B keeps the same
         bool failed = false;
         for (uint32_t b = 0;; b++) {
             const int s = b & 1;
@@ -524,13 +572,32 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
             }
             // (the rendezvous with B below keeps this warp exactly one batch ahead of B, which is what B's "source still in
             // the ring" test assumes)
+            // ---- far back-references.  A source that has left the ring (more than kRing - kMaxBatchOut bytes behind the end of
+            // this batch, or inside a bypassed literal) was written to HBM by warp B long ago: B is at most one batch behind
+            // this warp and lags its own output by < kFlushBytes, so everything below dst0 - kMaxBatchOut - kFlushBytes is in
+            // global memory and visible (rendezvous on kBarAB).  Such a copy depends on nothing in flight: this warp fetches
+            // it like a literal - the loads are issued here, overlap the literal placement below, and the bytes go into the
+            // ring before the hand-over - instead of B doing it one lane at a time with a flush in front (r2final: 5 % of
+            // the C2 back-references, 3.8 % of the kernel's instructions and most of B's batch-to-batch variance).
+            bool far_mine = false;
+            uint32_t far_v[8];
+            const uint8_t *far_g = dst;
+            if (!failed) {
+                const uint32_t sp = d - a;
+                const bool in_ring = sp >= valid_from && dst0 + total - sp <= (uint32_t)kRing - kMaxBatchOut;
+                const uint32_t lag = kMaxBatchOut + kFlushBytes;
+                const uint32_t in_hbm = max(valid_from, dst0 > lag ? dst0 - lag : 0u);   // positions below this are flushed
+                far_mine = is_copy && !in_ring && sp + len <= in_hbm;
+                if (far_mine) {
+                    far_g = dst + sp;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) far_v[k] = (uint32_t)k < len ? (uint32_t)__ldcg(far_g + k) : 0u;
+                }
+            }
             if (!failed) {
                 // ---- literals: staging -> ring.  Short ones per lane, longer ones by the whole warp.
                 const bool is_lit = have && kind == 0;
-                if (is_lit && len <= 16) {
-                    for (uint32_t i = 0; i < len; i++)
-                        sts_u8(ring_s + ((d + i) & kRingMask), lds_u8(stage_s + ((a + i) & kStageMask)));
-                }
+                if (is_lit && len <= 16) smem_bytes(stage_s, kStageMask, a, ring_s, kRingMask, d, len, true);
                 uint32_t longs = __ballot_sync(0xffffffffu, is_lit && len > 16);
                 while (longs) {
                     const int l = __ffs(longs) - 1;
@@ -542,14 +609,24 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                         sts_u8(ring_s + ((bd + i) & kRingMask), lds_u8(stage_s + ((ba + i) & kStageMask)));
                 }
             }
+            if (far_mine) {
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if ((uint32_t)k < len) sts_u8(ring_s + ((d + (uint32_t)k) & kRingMask), far_v[k]);
+                for (uint32_t i = 8; i < len; i++)
+                    sts_u8(ring_s + ((d + i) & kRingMask), (uint32_t)__ldcg(far_g + i));
+            }
             sts_u32(ex_s + 4u * lane, d);
             sts_u32(ex_s + 128u + 4u * lane, a);
-            sts_u32(ex_s + 256u + 4u * lane, (is_copy && !failed) ? len : 0u);
+            sts_u32(ex_s + 256u + 4u * lane, (is_copy && !failed && !far_mine) ? len : 0u);
             if (lane == 0) {
                 sts_v4(ex_s + kExecHdr, dst0 + total, has_big && !failed ? big_len : 0u, rare.x, last);
                 sts_v2(ex_s + kExecHdr + 16, failed ? 1u : 0u, dst0);
             }
-            if (!failed) dst0 += total + (has_big ? big_len : 0u);
+            if (!failed) {
+                dst0 += total + (has_big ? big_len : 0u);
+                if (has_big) valid_from = dst0;
+            }
             __syncwarp();
             __threadfence_block();
             if (big_len != 0 && !last) bar_sync_imm<kBarPA>();   // P may move the staging window now
@@ -595,11 +672,14 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                 const bool in_ring = sp >= valid_from && dst_end - sp <= (uint32_t)kRing - kMaxBatchOut;
                 // the common case first: a source that ends in front of the batch depends on nothing in it
                 const bool early = is_copy && in_ring && src_end <= dst_begin;
-                if (early) {
-                    for (uint32_t i = 0; i < len; i++)
-                        sts_u8(ring_s + ((d + i) & kRingMask), lds_u8(ring_s + ((d + i - a) & kRingMask)));
+                if (early) smem_bytes(ring_s, kRingMask, d - a, ring_s, kRingMask, d, len, a >= 4u);
+                // a source outside the ring that this warp has already written to HBM depends on nothing either (warp A
+                // takes most of these; what is left are sources next to a bypassed literal)
+                const bool far_done = is_copy && !in_ring && sp + len <= flushed;
+                if (far_done) {
+                    for (uint32_t i = 0; i < len; i++) sts_u8(ring_s + ((d + i) & kRingMask), (uint32_t)__ldcg(dst + sp + i));
                 }
-                uint32_t pending = __ballot_sync(0xffffffffu, is_copy && !early);
+                uint32_t pending = __ballot_sync(0xffffffffu, is_copy && !early && !far_done);
                 __syncwarp();
                 while (pending) {
                     const int first = __ffs(pending) - 1;
@@ -619,11 +699,8 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                             }
                         }
                     }
-                    if (ready && in_ring) {
-                        // sequential per lane: an overlapping copy (offset < length) re-reads its own bytes
-                        for (uint32_t i = 0; i < len; i++)
-                            sts_u8(ring_s + ((d + i) & kRingMask), lds_u8(ring_s + ((d + i - a) & kRingMask)));
-                    }
+                    // sequential per lane: an overlapping copy (offset < length) re-reads its own bytes
+                    if (ready && in_ring) smem_bytes(ring_s, kRingMask, d - a, ring_s, kRingMask, d, len, a >= 4u);
                     pending &= ~__ballot_sync(0xffffffffu, ready);
                     __syncwarp();
                 }
@@ -670,7 +747,10 @@ constexpr int kIdxBuilders = 12;
 constexpr int kIdxThreads = 32 * (kIdxBuilders + 1);
 constexpr int kIdxW = 1024;
 constexpr int kIdxPad = 64;
-constexpr int kIdxRounds = 6;          // a table entry covers 2^kIdxRounds elements: the walker (the serial part) does one
+#ifndef PST_IDX_ROUNDS
+#define PST_IDX_ROUNDS 6
+#endif
+constexpr int kIdxRounds = PST_IDX_ROUNDS;          // a table entry covers 2^kIdxRounds elements: the walker (the serial part) does one
                                        // shared-memory load per 64 elements; the twelve builders absorb the extra rounds
 constexpr size_t kIdxSmemBytes = (size_t)2 * kIdxBuilders * (kIdxW + kIdxPad) * sizeof(uint32_t);
 
@@ -842,6 +922,22 @@ k_snappy_index(const uint8_t *__restrict__ arena, const DevPage *__restrict__ pa
                 for (;;) {
                     // the chain: one LDS + two adds per 16 elements; forward exits only, one backward branch per 4 hops
                     uint32_t a = base + (ip << 2), e, adv;
+                    // far from the next fragment boundary (an entry produces at most kIdxEntryOut bytes) the chain needs no
+                    // test per hop: LDS -> mask -> add, four hops per round; a zero entry is a fixed point, so a stall
+                    // inside the round shows in its last entry and neither `a` nor `op` moved past it
+                    constexpr uint32_t kIdxEntryOut = 64u << kIdxRounds;
+                    while (next_b - op > 4u * kIdxEntryOut) {
+                        const uint32_t e1 = lds_u32(a);
+                        a += e1 & 0xffffu;
+                        const uint32_t e2 = lds_u32(a);
+                        a += e2 & 0xffffu;
+                        const uint32_t e3 = lds_u32(a);
+                        a += e3 & 0xffffu;
+                        const uint32_t e4 = lds_u32(a);
+                        a += e4 & 0xffffu;
+                        op += (e1 >> 16) + (e2 >> 16) + (e3 >> 16) + (e4 >> 16);
+                        if ((e4 & 0xffffu) == 0) break;
+                    }
                     for (;;) {
                         bool out = false;
 #pragma unroll

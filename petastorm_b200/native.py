@@ -10,7 +10,7 @@ from ctypes import (POINTER, Structure, byref, c_char_p, c_double, c_float, c_in
                     c_uint8, c_uint64, c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libpst_b200.so')
+LIB_PATH = os.environ.get('PST_B200_LIB') or os.path.join(_HERE, 'libpst_b200.so')   # override: kernel experiments
 
 
 class NativeLibraryError(RuntimeError):
