@@ -643,7 +643,11 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
                      [&](const SnFrag &a, const SnFrag &b) { return ratio_less(a.page, b.page); });
     {   // same order for the index kernel; multi_slot follows the sorted list
         std::stable_sort(p->multi_pages.begin(), p->multi_pages.end(), ratio_less);
-        std::stable_sort(p->index_pages.begin(), p->index_pages.end(), ratio_less);
+        // the index kernel spends one CTA per page and its time goes with the page's compressed size: longest first, so
+        // that the launch does not end on a 1 MiB dictionary page that started in the second wave
+        std::stable_sort(p->index_pages.begin(), p->index_pages.end(), [&](int32_t a, int32_t b) {
+            return p->pages[a].d.comp_size > p->pages[b].d.comp_size;
+        });
         for (size_t i = 0; i < p->multi_pages.size(); i++) p->pages[p->multi_pages[i]].d.multi_slot = (int32_t)i;
     }
 

@@ -200,6 +200,7 @@ __device__ __forceinline__ void smem_bytes(uint32_t src_s, uint32_t smask, uint3
         if (r > 2) sts_u8_off<2>(da, lds_u8_off<2>(sa));
         return;
     }
+#pragma unroll 1
     for (uint32_t i = 0; i < len; i++) sts_u8(dst_s + ((d + i) & dmask), lds_u8(src_s + ((sp + i) & smask)));
 }
 // Hand-over between the stages is a RENDEZVOUS on one named barrier per pair of warps: when P and A meet, P has finished
@@ -224,6 +225,25 @@ struct SnExec {                 // warp A -> warp B: the back-references of one 
 };
 static_assert(sizeof(SnExec) == 416, "SnExec layout");
 constexpr uint32_t kExecHdr = kBatchOps * 12;
+
+// ---- code that runs rarely is kept OUT of line.  The three warps of a CTA execute three different loops and seven CTAs
+// share an SM: the decoder turned out to be sensitive to its instruction-cache footprint (r2l captures: a variant that
+// executed 6 % fewer instructions but was 10 KB longer lost 24 % to `no_instructions` stalls).
+// ring -> HBM write-through of output positions [from, to), to - from <= kRing; ring and dst agree modulo 16.
+__device__ __noinline__ void snappy_ring_flush(uint8_t *dst, uint32_t ring_s, uint32_t from, uint32_t to) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t body0 = min((from + 15u) & ~15u, to), body1 = max(to & ~15u, body0);
+    if (from + lane < body0) dst[from + lane] = (uint8_t)lds_u8(ring_s + ((from + lane) & kRingMask));      // < 16 bytes
+    if (body1 + lane < to) dst[body1 + lane] = (uint8_t)lds_u8(ring_s + ((body1 + lane) & kRingMask));      // < 16 bytes
+#pragma unroll 2
+    for (uint32_t q = body0 + 16u * lane; q < body1; q += 512u) {
+        const uint4 v = lds_v4(ring_s + (q & kRingMask));
+        *reinterpret_cast<uint4 *>(dst + q) = v;
+    }
+}
+__device__ __noinline__ void snappy_warp_copy_cold(uint8_t *dst, const uint8_t *src, uint32_t n) {
+    coop_copy(dst, src, n, (int)(threadIdx.x & 31u), 32);
+}
 
 __global__ void __launch_bounds__(kSnappyThreads)
 k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, const SnFrag *__restrict__ frags,
@@ -281,7 +301,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
     // V2 data pages: the level bytes are stored uncompressed in front of the compressed values
     if (pg.kind == PK_DATA_V2) {
         uint32_t lv = (uint32_t)(pg.def_bytes + pg.rep_bytes);
-        if (warp == 1 && frag_k == 0) coop_copy(dst, src, lv, lane, 32);
+        if (warp == 1 && frag_k == 0) snappy_warp_copy_cold(dst, src, lv);
         src += lv; dst += lv; src_n -= lv; dst_n -= lv;
     }
     const uint32_t full_n = dst_n;            // the length the stream's preamble must announce
@@ -375,26 +395,23 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                 const uint32_t tag0 = lds_u8(stage_s + (ip & kStageMask));
                 if (lds_u8(lut_s + tag0) != 0) {   // a window that starts with a slow-path element is not worth a build
                     const uint32_t w0 = ip & ~3u;
-                    // (volatile asm accessors execute in program order: batch the loads, then use them)
-                    {
-                        uint32_t word[kTabW / 128];
+                    // (rolled: this runs once per ~9 batches and straight-line code would only evict the hot loops from the
+                    // instruction cache)
+#pragma unroll 1
+                    for (int h = 0; h < kTabW / 128; h += 2) {
+                        uint32_t word[2], e[8];
 #pragma unroll
-                        for (int k = 0; k < kTabW / 128; k++)
-                            word[k] = lds_u32(stage_s + ((w0 + 4u * ((uint32_t)lane + 32u * (uint32_t)k)) & kStageMask));
+                        for (int q = 0; q < 2; q++)
+                            word[q] = lds_u32(stage_s + ((w0 + 4u * ((uint32_t)lane + 32u * (uint32_t)(h + q))) & kStageMask));
 #pragma unroll
-                        for (int h = 0; h < kTabW / 128; h += 2) {
-                            uint32_t e[8];
+                        for (int q = 0; q < 8; q++) e[q] = lds_u8(lut_s + ((word[q >> 2] >> (8 * (q & 3))) & 0xffu));
 #pragma unroll
-                            for (int q = 0; q < 8; q++)
-                                e[q] = lds_u8(lut_s + ((word[h + (q >> 2)] >> (8 * (q & 3))) & 0xffu));
-#pragma unroll
-                            for (int q = 0; q < 2; q++) {
-                                const uint32_t wi = (uint32_t)lane + 32u * (uint32_t)(h + q);
-                                uint32_t st = e[4 * q] | (e[4 * q + 1] << 8) | (e[4 * q + 2] << 16) | (e[4 * q + 3] << 24);
-                                const int32_t nv = (int32_t)(in_end - (w0 + 4u * wi));
-                                if (nv < 4) st = nv <= 0 ? 0u : (st & ((1u << (8 * nv)) - 1u));
-                                sts_u32(step_s + 4u * wi, st);
-                            }
+                        for (int q = 0; q < 2; q++) {
+                            const uint32_t wi = (uint32_t)lane + 32u * (uint32_t)(h + q);
+                            uint32_t st = e[4 * q] | (e[4 * q + 1] << 8) | (e[4 * q + 2] << 16) | (e[4 * q + 3] << 24);
+                            const int32_t nv = (int32_t)(in_end - (w0 + 4u * wi));
+                            if (nv < 4) st = nv <= 0 ? 0u : (st & ((1u << (8 * nv)) - 1u));
+                            sts_u32(step_s + 4u * wi, st);
                         }
                     }
                     __syncwarp();
@@ -452,6 +469,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                     } else if ((tag & 3) == 0 && t6 >= 60) {
                         const uint32_t nb = t6 - 59;
                         uint32_t v = 0;
+#pragma unroll 1
                         for (uint32_t i = 0; i < nb; i++) v |= IN(ip + 1 + i) << (8 * i);
                         const uint32_t len = v + 1;
                         const uint32_t p0 = ip + 1 + nb;
@@ -613,6 +631,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
 #pragma unroll
                 for (int k = 0; k < 8; k++)
                     if ((uint32_t)k < len) sts_u8(ring_s + ((d + (uint32_t)k) & kRingMask), far_v[k]);
+#pragma unroll 1
                 for (uint32_t i = 8; i < len; i++)
                     sts_u8(ring_s + ((d + i) & kRingMask), (uint32_t)__ldcg(far_g + i));
             }
@@ -645,11 +664,9 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
         uint32_t flushed = bias;      // output positions below this are already in global memory
         uint32_t valid_from = bias;      // output positions below this are not in the ring (bypassed literal)
         auto flush_to = [&](uint32_t t) {
-            while (flushed < t) {
-                const uint32_t r = flushed & kRingMask;
-                const uint32_t nn = min(t - flushed, (uint32_t)kRing - r);
-                coop_copy(dst + flushed, ring + r, nn, lane, 32);
-                flushed += nn;
+            if (flushed < t) {
+                snappy_ring_flush(dst, ring_s, flushed, t);
+                flushed = t;
             }
         };
         for (uint32_t b = 0;; b++) {
@@ -677,6 +694,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                 // takes most of these; what is left are sources next to a bypassed literal)
                 const bool far_done = is_copy && !in_ring && sp + len <= flushed;
                 if (far_done) {
+#pragma unroll 1
                     for (uint32_t i = 0; i < len; i++) sts_u8(ring_s + ((d + i) & kRingMask), (uint32_t)__ldcg(dst + sp + i));
                 }
                 uint32_t pending = __ballot_sync(0xffffffffu, is_copy && !early && !far_done);
@@ -693,6 +711,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                         flush_to(done_pos);
                         __syncwarp();
                         if (lane == first) {
+#pragma unroll 1
                             for (uint32_t i = 0; i < len; i++) {
                                 const uint32_t q = sp + i;
                                 ring[(d + i) & kRingMask] = q < done_pos ? dst[q] : ring[q & kRingMask];
@@ -707,7 +726,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                 uint32_t dst0 = dst_end;
                 if (big_len) {      // bypassed big literal (always behind the last element of its batch)
                     flush_to(dst0);
-                    coop_copy(dst + dst0, gin + big_src, big_len, lane, 32);
+                    snappy_warp_copy_cold(dst + dst0, gin + big_src, big_len);
                     dst0 += big_len;
                     flushed = dst0;
                     valid_from = dst0;
