@@ -53,9 +53,14 @@ namespace pst {
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane);   // defined with the page decoder below
 
 constexpr int kSnappyThreads = 96;      // parser warp, placement warp, copy warp
-constexpr int kRing = 16384;          // power of two; with staging and tables ~31 KiB of shared memory per CTA (7 CTAs/SM).
-// (8 KiB was measured: 9 CTAs/SM, but 8% of the back-references of the C2 int64 pages then reach behind the ring
-// and take the slow path through HBM -- 1.66 ms instead of 1.38 ms per row-group.)
+#ifndef PST_RING
+#define PST_RING 8192
+#endif
+constexpr int kRing = PST_RING;          // power of two; with staging and tables ~23 KiB of shared memory per CTA (9 CTAs/SM).
+// (History: in round 1 an 8 KiB ring lost to 16 KiB - 1.66 against 1.38 ms per C2 row-group - because 8 % of the
+// back-references of the int64 pages then reach behind the ring and went through a serial path with a flush in front.
+// Since every lane fetches such a source from HBM on its own (warp B) the occupancy wins: 0.99 ms with 16 KiB and
+// 7 CTAs/SM, 0.83 ms with 8 KiB and 9 CTAs/SM.)
 constexpr uint32_t kRingMask = kRing - 1;
 constexpr int kStage = 8192;          // input staging window: 4 chunks of 2 KiB (power of two)
 constexpr uint32_t kStageMask = kStage - 1;
@@ -65,7 +70,7 @@ constexpr int kBatchOps = 32;
 constexpr uint32_t kBatchIn = 2048;   // >= input span of a batch without its last element (32 elements x <= 62 bytes)
 // (output per batch is bounded by the two limits above: 32 copies x 64 B + < 2 KiB of literals)
 constexpr uint32_t kBigLiteral = 1024;
-constexpr uint32_t kFlushBytes = 4096;   // kFlushBytes + 2 * kMaxBatchOut <= kRing: A never overwrites unflushed bytes
+constexpr uint32_t kFlushBytes = PST_RING >= 16384 ? 4096 : 2048;   // kFlushBytes + 2 * kMaxBatchOut <= kRing: A never overwrites unflushed bytes
 constexpr uint32_t kLookahead = kBatchIn + kBigLiteral + 8;   // staged bytes a batch may touch past its start
 
 constexpr int kHops = kBatchOps / 4;   // the parser advances four elements per step ("hop")
@@ -82,7 +87,10 @@ struct SnBatch {
 static_assert(sizeof(SnBatch) == 96, "SnBatch layout");
 constexpr uint32_t kHdrOff = kHops * 8;
 // successor tables of the parser (see warp P)
-constexpr int kTabW = 1024;           // input positions covered by one table build (static shared memory <= 48 KiB)
+#ifndef PST_TABW
+#define PST_TABW 1024
+#endif
+constexpr int kTabW = PST_TABW;           // input positions covered by one table build (static shared memory <= 48 KiB)
 constexpr int kTabPad = 64;           // zero entries behind the window: an element is at most 61 bytes long
 
 
@@ -210,6 +218,7 @@ constexpr int kBarPA = 1;
 constexpr int kBarAB = 2;
 // output bytes of one batch: 32 elements of <= 64 bytes plus a staged long literal (< kBigLiteral)
 constexpr uint32_t kMaxBatchOut = kBatchOps * 64 + kBigLiteral;
+static_assert(kFlushBytes + 2 * kMaxBatchOut <= (uint32_t)kRing, "warp A must never overwrite unflushed ring bytes");
 
 struct SnExec {                 // warp A -> warp B: the back-references of one batch, positions already assigned
     uint32_t d[kBatchOps];      // output position
@@ -245,7 +254,10 @@ __device__ __noinline__ void snappy_warp_copy_cold(uint8_t *dst, const uint8_t *
     coop_copy(dst, src, n, (int)(threadIdx.x & 31u), 32);
 }
 
-__global__ void __launch_bounds__(kSnappyThreads)
+#ifndef PST_SNAPPY_MIN_CTAS
+#define PST_SNAPPY_MIN_CTAS 9
+#endif
+__global__ void __launch_bounds__(kSnappyThreads, PST_SNAPPY_MIN_CTAS)
 k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, const SnFrag *__restrict__ frags,
                int n_frags, const int32_t *__restrict__ multi_list, int n_multi, const uint32_t *__restrict__ frag_pos,
                uint32_t *page_flag, int32_t *status, int serial_mode) {
@@ -520,7 +532,6 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
         const uint32_t ring_s = shared_addr(ring), stage_s = shared_addr(stage), batches_s = shared_addr(&batches[0]);
         const uint32_t execs_s = shared_addr(&execs[0]);
         uint32_t dst0 = bias;         // output position of the next batch
-        uint32_t valid_from = bias;   // output positions below this never were in the ring (bypassed literal); B keeps the same
         bool failed = false;
         for (uint32_t b = 0;; b++) {
             const int s = b & 1;
@@ -590,28 +601,6 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
             }
             // (the rendezvous with B below keeps this warp exactly one batch ahead of B, which is what B's "source still in
             // the ring" test assumes)
-            // ---- far back-references.  A source that has left the ring (more than kRing - kMaxBatchOut bytes behind the end of
-            // this batch, or inside a bypassed literal) was written to HBM by warp B long ago: B is at most one batch behind
-            // this warp and lags its own output by < kFlushBytes, so everything below dst0 - kMaxBatchOut - kFlushBytes is in
-            // global memory and visible (rendezvous on kBarAB).  Such a copy depends on nothing in flight: this warp fetches
-            // it like a literal - the loads are issued here, overlap the literal placement below, and the bytes go into the
-            // ring before the hand-over - instead of B doing it one lane at a time with a flush in front (r2final: 5 % of
-            // the C2 back-references, 3.8 % of the kernel's instructions and most of B's batch-to-batch variance).
-            bool far_mine = false;
-            uint32_t far_v[8];
-            const uint8_t *far_g = dst;
-            if (!failed) {
-                const uint32_t sp = d - a;
-                const bool in_ring = sp >= valid_from && dst0 + total - sp <= (uint32_t)kRing - kMaxBatchOut;
-                const uint32_t lag = kMaxBatchOut + kFlushBytes;
-                const uint32_t in_hbm = max(valid_from, dst0 > lag ? dst0 - lag : 0u);   // positions below this are flushed
-                far_mine = is_copy && !in_ring && sp + len <= in_hbm;
-                if (far_mine) {
-                    far_g = dst + sp;
-#pragma unroll
-                    for (int k = 0; k < 8; k++) far_v[k] = (uint32_t)k < len ? (uint32_t)__ldcg(far_g + k) : 0u;
-                }
-            }
             if (!failed) {
                 // ---- literals: staging -> ring.  Short ones per lane, longer ones by the whole warp.
                 const bool is_lit = have && kind == 0;
@@ -627,25 +616,14 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                         sts_u8(ring_s + ((bd + i) & kRingMask), lds_u8(stage_s + ((ba + i) & kStageMask)));
                 }
             }
-            if (far_mine) {
-#pragma unroll
-                for (int k = 0; k < 8; k++)
-                    if ((uint32_t)k < len) sts_u8(ring_s + ((d + (uint32_t)k) & kRingMask), far_v[k]);
-#pragma unroll 1
-                for (uint32_t i = 8; i < len; i++)
-                    sts_u8(ring_s + ((d + i) & kRingMask), (uint32_t)__ldcg(far_g + i));
-            }
             sts_u32(ex_s + 4u * lane, d);
             sts_u32(ex_s + 128u + 4u * lane, a);
-            sts_u32(ex_s + 256u + 4u * lane, (is_copy && !failed && !far_mine) ? len : 0u);
+            sts_u32(ex_s + 256u + 4u * lane, (is_copy && !failed) ? len : 0u);
             if (lane == 0) {
                 sts_v4(ex_s + kExecHdr, dst0 + total, has_big && !failed ? big_len : 0u, rare.x, last);
                 sts_v2(ex_s + kExecHdr + 16, failed ? 1u : 0u, dst0);
             }
-            if (!failed) {
-                dst0 += total + (has_big ? big_len : 0u);
-                if (has_big) valid_from = dst0;
-            }
+            if (!failed) dst0 += total + (has_big ? big_len : 0u);
             __syncwarp();
             __threadfence_block();
             if (big_len != 0 && !last) bar_sync_imm<kBarPA>();   // P may move the staging window now
@@ -690,12 +668,23 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                 // the common case first: a source that ends in front of the batch depends on nothing in it
                 const bool early = is_copy && in_ring && src_end <= dst_begin;
                 if (early) smem_bytes(ring_s, kRingMask, d - a, ring_s, kRingMask, d, len, a >= 4u);
-                // a source outside the ring that this warp has already written to HBM depends on nothing either (warp A
-                // takes most of these; what is left are sources next to a bypassed literal)
+                // a source outside the ring that this warp has already written to HBM depends on nothing either: every lane
+                // fetches its own.  (5 % of the C2 back-references.  The first version handled them one lane at a time in
+                // the dependency rounds with a flush in front - 3.8 % of the kernel's instructions and most of this warp's
+                // batch-to-batch variance; fetching them in warp A like literals was 6 % slower than this, A being the
+                // busiest of the three warps.)
                 const bool far_done = is_copy && !in_ring && sp + len <= flushed;
                 if (far_done) {
+                    // (loads first: one L2 round trip for the first eight bytes instead of one per byte)
+                    const uint8_t *g = dst + sp;
+                    uint32_t v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) v[k] = (uint32_t)k < len ? (uint32_t)__ldcg(g + k) : 0u;
+#pragma unroll
+                    for (int k = 0; k < 8; k++)
+                        if ((uint32_t)k < len) sts_u8(ring_s + ((d + (uint32_t)k) & kRingMask), v[k]);
 #pragma unroll 1
-                    for (uint32_t i = 0; i < len; i++) sts_u8(ring_s + ((d + i) & kRingMask), (uint32_t)__ldcg(dst + sp + i));
+                    for (uint32_t i = 8; i < len; i++) sts_u8(ring_s + ((d + i) & kRingMask), (uint32_t)__ldcg(g + i));
                 }
                 uint32_t pending = __ballot_sync(0xffffffffu, is_copy && !early && !far_done);
                 __syncwarp();
