@@ -88,9 +88,9 @@ static_assert(sizeof(SnBatch) == 96, "SnBatch layout");
 constexpr uint32_t kHdrOff = kHops * 8;
 // successor tables of the parser (see warp P)
 #ifndef PST_TABW
-#define PST_TABW 1024
+#define PST_TABW 768
 #endif
-constexpr int kTabW = PST_TABW;           // input positions covered by one table build (static shared memory <= 48 KiB)
+constexpr int kTabW = PST_TABW;           // input positions covered by one table build (multiple of 256; 768: 10 CTAs/SM)
 constexpr int kTabPad = 64;           // zero entries behind the window: an element is at most 61 bytes long
 
 
@@ -255,7 +255,7 @@ __device__ __noinline__ void snappy_warp_copy_cold(uint8_t *dst, const uint8_t *
 }
 
 #ifndef PST_SNAPPY_MIN_CTAS
-#define PST_SNAPPY_MIN_CTAS 9
+#define PST_SNAPPY_MIN_CTAS 10
 #endif
 __global__ void __launch_bounds__(kSnappyThreads, PST_SNAPPY_MIN_CTAS)
 k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, const SnFrag *__restrict__ frags,
@@ -1145,6 +1145,101 @@ __device__ void hybrid_scan(HybridCursor &c, RunTable &t, uint32_t want) {
     t.filled = filled;
 }
 
+// Warp version of hybrid_scan for long index streams (dictionary fast path of k_decode_pages).  Walking the headers is
+// a chain of dependent loads from HBM/L2 - one per run, ~0.2 us each - and the writers emit long sequences of IDENTICAL
+// bit-packed runs (Arrow: 64 groups = 512 values per header byte).  So the warp speculates: once a bit-packed header is
+// known, lane l reads the header that would follow l runs of the same shape; the leading lanes that find the same header
+// again are runs whose position is thereby proven, and all of them enter the table at the price of two loads.  Anything
+// else (RLE runs, the odd last run) is decoded one header at a time as before.  All lanes run the same control flow on the
+// same cursor values; lane 0 writes the cursor back.
+__device__ __forceinline__ bool hybrid_header(const uint8_t *q, const uint8_t *end, uint32_t &h, uint32_t &hlen) {
+    h = 0;
+    hlen = 0;
+    int shift = 0;
+    for (;;) {
+        if (q + hlen >= end || shift > 28) return false;
+        const uint8_t b = q[hlen++];
+        h |= (uint32_t)(b & 0x7f) << shift;
+        if (!(b & 0x80)) return true;
+        shift += 7;
+    }
+}
+__device__ void hybrid_scan_warp(HybridCursor &c, RunTable &t, uint32_t want, int lane) {
+    const uint8_t *p = c.p, *const end = c.end, *bp_ptr = c.bp_ptr;
+    uint32_t bp_index = c.bp_index, remaining = c.remaining, rle_value = c.rle_value;
+    const int bw = c.bw;
+    int kind = c.kind, n = 0, error = 0;
+    uint32_t filled = 0;
+    while (filled < want && n < kRunCap) {
+        if (remaining == 0) {
+            uint32_t h0, hlen0;
+            if (!hybrid_header(p, end, h0, hlen0)) { error = 1; break; }
+            const uint32_t count0 = (h0 >> 1) * 8u;
+            if ((h0 & 1u) && count0 != 0) {
+                // ---- a sequence of identical bit-packed runs
+                const uint64_t stride = (uint64_t)hlen0 + (uint64_t)(h0 >> 1) * (uint64_t)bw;
+                const uint8_t *q = p + (uint64_t)lane * stride;
+                uint32_t h = 0, hlen = 0;
+                const bool same = lane == 0 || (q < end && hybrid_header(q, end, h, hlen) && h == h0 && hlen == hlen0);
+                const uint32_t miss = ~__ballot_sync(0xffffffffu, same);
+                uint32_t k = miss ? (uint32_t)(__ffs(miss) - 1) : 32u;                  // proven runs
+                k = min(k, (uint32_t)(kRunCap - n));
+                k = min(k, (want - filled + count0 - 1) / count0);                       // runs needed
+                if ((uint32_t)lane < k) {
+                    RunEntry &e = t.e[n + lane];
+                    e.ptr = q + hlen0;
+                    e.out_start = filled + (uint32_t)lane * count0;
+                    e.count = min(count0, want - e.out_start);
+                    e.value_or_index = 0;
+                    e.is_rle = 0;
+                }
+                const uint32_t got = min(k * count0, want - filled);
+                const uint32_t last_take = got - (k - 1) * count0;                       // values taken from the last run
+                n += (int)k;
+                filled += got;
+                p += (uint64_t)k * stride;
+                kind = 2;
+                bp_ptr = p - (stride - hlen0);
+                bp_index = last_take;
+                remaining = count0 - last_take;
+                continue;
+            }
+            p += hlen0;
+            if (h0 & 1u) continue;                       // empty bit-packed run (legal, useless)
+            kind = 1;
+            remaining = h0 >> 1;
+            const int nb = (bw + 7) >> 3;
+            uint32_t v = 0;
+            if (p + nb > end) { error = 1; break; }
+            for (int i = 0; i < nb; i++) v |= (uint32_t)p[i] << (8 * i);
+            p += nb;
+            rle_value = v;
+            if (remaining == 0) continue;
+        }
+        const uint32_t take = min(remaining, want - filled);
+        if (lane == 0) {
+            RunEntry &e = t.e[n];
+            e.out_start = filled;
+            e.count = take;
+            e.is_rle = kind == 1 ? 1u : 0u;
+            e.value_or_index = kind == 1 ? rle_value : bp_index;
+            e.ptr = kind == 1 ? nullptr : bp_ptr;
+        }
+        n++;
+        if (kind != 1) bp_index += take;
+        remaining -= take;
+        filled += take;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        c.p = p; c.bp_ptr = bp_ptr; c.bp_index = bp_index; c.remaining = remaining; c.rle_value = rle_value;
+        c.kind = kind;
+        if (error) c.error = 1;
+        t.n = n;
+        t.filled = filled;
+    }
+}
+
 // All threads: produce exactly `want` values of the stream into dst[0..want) (shared memory, uint32).
 // Returns false (uniformly) on a corrupt stream.
 __device__ bool hybrid_fill(HybridCursor &c, RunTable &t, uint32_t *dst, uint32_t want) {
@@ -1342,7 +1437,7 @@ k_decode_pages(uint8_t *__restrict__ arena, uint8_t *__restrict__ out, const Dev
         const uint32_t dict_count = (uint32_t)col.dict_count;
         while (done < nvals) {
             __syncthreads();
-            if (tid == 0) hybrid_scan(sh.idx_c, sh.table, nvals - done);
+            if (warp == 0) hybrid_scan_warp(sh.idx_c, sh.table, nvals - done, lane);
             __syncthreads();
             if (sh.idx_c.error || sh.table.filled == 0) {
                 if (tid == 0) report_error(status, DE_LEVELS_CORRUPT, pi, 12);
