@@ -1446,17 +1446,46 @@ k_decode_pages(uint8_t *__restrict__ arena, uint8_t *__restrict__ out, const Dev
             const int n = sh.table.n;
             const uint32_t filled = sh.table.filled;
             const int bw = sh.idx_c.bw;
+            // four values per thread and round: the index words come from HBM and the dictionary entries from L2/HBM, and
+            // with one value in flight per thread 74 % of the warp samples were waits on these two loads (r2t capture)
             int ei = 0;
-            for (uint32_t i = tid; i < filled; i += kDecThreads) {
-                while (ei + 1 < n && sh.table.e[ei + 1].out_start <= i) ei++;
-                const RunEntry &e = sh.table.e[ei];
-                uint32_t di = e.is_rle ? e.value_or_index
-                                       : extract_bits(e.ptr, (uint64_t)(e.value_or_index + (i - e.out_start)) * bw, bw);
-                if (di >= dict_count) { report_error(status, DE_DICT_INDEX_RANGE, pi, (int)di); di = 0; }
-                const int64_t row = first + done + i;
-                if (W == 4) reinterpret_cast<uint32_t *>(o_values)[row] = reinterpret_cast<const uint32_t *>(dict)[di];
-                else reinterpret_cast<uint64_t *>(o_values)[row] = reinterpret_cast<const uint64_t *>(dict)[di];
+            bool range_err = false;
+            for (uint32_t i0 = tid; i0 < filled; i0 += 4 * kDecThreads) {
+                uint32_t di[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t i = i0 + (uint32_t)u * kDecThreads;
+                    di[u] = 0;
+                    if (i < filled) {
+                        while (ei + 1 < n && sh.table.e[ei + 1].out_start <= i) ei++;
+                        const RunEntry &e = sh.table.e[ei];
+                        di[u] = e.is_rle ? e.value_or_index
+                                         : extract_bits(e.ptr, (uint64_t)(e.value_or_index + (i - e.out_start)) * bw, bw);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (di[u] >= dict_count) { range_err = true; di[u] = 0; }
+                const int64_t row = first + done + i0;
+                if (W == 4) {
+                    uint32_t v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) v[u] = reinterpret_cast<const uint32_t *>(dict)[di[u]];
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (i0 + (uint32_t)u * kDecThreads < filled)
+                            reinterpret_cast<uint32_t *>(o_values)[row + u * kDecThreads] = v[u];
+                } else {
+                    uint64_t v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) v[u] = reinterpret_cast<const uint64_t *>(dict)[di[u]];
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (i0 + (uint32_t)u * kDecThreads < filled)
+                            reinterpret_cast<uint64_t *>(o_values)[row + u * kDecThreads] = v[u];
+                }
             }
+            if (range_err) report_error(status, DE_DICT_INDEX_RANGE, pi, 0);
             done += filled;
         }
         if (o_valid) coop_fill(o_valid + first, 1, nvals, tid, kDecThreads);
