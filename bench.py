@@ -554,8 +554,18 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     cores = os.cpu_count() or 1
     if args.workload == 'c2':
-        return run_c2(args, rank, local_rank, world, cores)
-    return run_rows(args, ROW_WORKLOADS[args.workload](args.rows_per_group or None), rank, local_rank, world, cores)
+        fn, fargs = run_c2, (args, rank, local_rank, world, cores)
+    else:
+        fn, fargs = run_rows, (args, ROW_WORKLOADS[args.workload](args.rows_per_group or None), rank, local_rank, world, cores)
+    prof_path = os.environ.get('PST_BENCH_PROFILE')      # diagnostics: cProfile of the consumer (main) thread
+    if prof_path:
+        import cProfile
+        prof = cProfile.Profile()
+        try:
+            return prof.runcall(fn, *fargs)
+        finally:
+            prof.dump_stats(prof_path)
+    return fn(*fargs)
 
 
 def _dist_setup(local_rank, world):

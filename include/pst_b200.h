@@ -105,7 +105,8 @@ typedef struct pst_plan_info {
     int32_t num_snappy_fragments; /* work items of k_snappy_pages */
     int32_t num_host_indexed_pages; /* multi-fragment Snappy pages of literal-dominated streams (blob columns): the planner
                                        walks their few tags itself, the others go through k_snappy_index */
-    int32_t reserved_;
+    int32_t num_cluster_index_pages;/* of the pages the device indexes (num_index_pages): those of >= 256 KiB stored bytes,
+                                       indexed by one four-CTA cluster each (k_snappy_index_cluster) */
 } pst_plan_info;
 int pst_plan_get_info(const pst_plan *p, pst_plan_info *out);
 

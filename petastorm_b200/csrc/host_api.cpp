@@ -648,6 +648,10 @@ int pst_plan_create(const pst_file *f, int rg, const int *cols, int ncols, pst_p
         std::stable_sort(p->index_pages.begin(), p->index_pages.end(), [&](int32_t a, int32_t b) {
             return p->pages[a].d.comp_size > p->pages[b].d.comp_size;
         });
+        // pages of 256 KiB and more (dictionary pages, mostly) get four SMs each: k_snappy_index_cluster
+        p->index_big_count = 0;
+        for (int32_t pi : p->index_pages)
+            if (p->pages[pi].d.comp_size >= 256 * 1024) p->index_big_count++;
         for (size_t i = 0; i < p->multi_pages.size(); i++) p->pages[p->multi_pages[i]].d.multi_slot = (int32_t)i;
     }
 
@@ -805,6 +809,7 @@ int pst_plan_get_info(const pst_plan *p, pst_plan_info *out) {
     out->num_index_pages = (int32_t)p->index_pages.size();
     out->num_unwrapped_pages = (int32_t)p->unwrapped_pages;
     out->num_host_indexed_pages = (int32_t)p->host_indexed_pages;
+    out->num_cluster_index_pages = p->index_big_count;
     out->num_copy_tiles = (int32_t)p->copy_tiles.size();
     out->num_decode_pages = (int32_t)p->data_pages.size();
     out->num_snappy_fragments = (int32_t)p->snappy_frags.size();

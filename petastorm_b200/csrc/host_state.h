@@ -39,7 +39,9 @@ struct pst_plan {
     std::vector<pst::SnFrag> snappy_frags;   // (page, fragment) work items of the Snappy fragment kernel
     std::vector<int32_t> multi_pages;        // compressed pages with more than one fragment (indexed first)
     std::vector<int32_t> gzip_pages;         // page indices compressed with GZIP
-    std::vector<int32_t> index_pages;        // multi-fragment pages whose fragment positions the device has to find
+    std::vector<int32_t> index_pages;        // multi-fragment pages whose fragment positions the device has to find,
+                                             // longest first
+    int32_t index_big_count = 0;             // the first index_big_count of them go to the cluster variant of the kernel
     // BYTE_ARRAY dictionaries the planner indexed itself (pages the device sees uncompressed): entries per plan column
     std::vector<std::pair<int, std::vector<pst::BaDictEntry>>> host_dict_index;
     std::vector<pst::CopyTile> copy_tiles;   // work items of k_copy_tiles (PF_COPY pages, <= 64 KiB each)

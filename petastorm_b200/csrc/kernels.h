@@ -21,6 +21,9 @@ cudaError_t configure_decode_kernels();
 // (serial_mode 0), serial fallback for pages the first two flagged (serial_mode 1)
 cudaError_t launch_snappy_index(uint8_t *arena, const DevPage *pages, const int32_t *multi_list, int n_multi,
                                 uint32_t *frag_pos, uint32_t *page_flag, cudaStream_t s);
+// the same for big pages: one cluster of four CTAs per page (walker CTA + three builder CTAs, tables through DSMEM)
+cudaError_t launch_snappy_index_cluster(uint8_t *arena, const DevPage *pages, const int32_t *list, int n_list,
+                                        uint32_t *frag_pos, uint32_t *page_flag, cudaStream_t s);
 cudaError_t launch_snappy(uint8_t *arena, const DevPage *pages, const SnFrag *frags, int n_frags,
                           const int32_t *multi_list, int n_multi, const uint32_t *frag_pos, uint32_t *page_flag,
                           int32_t *status, int serial_mode, cudaStream_t s);

@@ -783,6 +783,262 @@ __device__ __forceinline__ void idx_mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+// thread-block cluster primitives (the big-page variant of the index kernel)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_map(uint32_t cta_addr, uint32_t rank) {      // shared::cta -> shared::cluster
+    uint32_t a;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(a) : "r"(cta_addr), "r"(rank));
+    return a;
+}
+__device__ __forceinline__ void cluster_sts_u32(uint32_t cluster_addr, uint32_t v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;\n" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_mbar_arrive(uint32_t cluster_bar) {          // release: publishes the caller's stores
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void cluster_mbar_arrive_relaxed(uint32_t cluster_bar) {  // a pure "I am done reading" signal
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_bar) : "memory");
+}
+// Waits on a LOCAL barrier whose arrivals come from other CTAs of the cluster.  A thread suspended in try_wait is not
+// woken by a remote arrival before its time limit runs out (r2w capture: builders and walker each waited ~6 us per
+// hand-over with the default limit and the cluster kernel was no faster than one SM), so the builders pass a short limit
+// and the walker - alone on its SM - polls with test_wait.
+__device__ __forceinline__ void cluster_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity), "r"(200u)       // suspend-time limit in ns
+            : "memory");
+    }
+}
+__device__ __forceinline__ void cluster_mbar_poll(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+// tag -> (bytes consumed * 4) | (bytes produced << 16); 0 = slow path (copy with a 4-byte offset, literal with a length suffix)
+__device__ __forceinline__ uint32_t idx_lut_entry(uint32_t t) {
+    const uint32_t kind = t & 3, t6 = t >> 2;
+    uint32_t used = 0, made = 0;
+    if (kind == 0) { if (t6 < 60) { used = t6 + 2; made = t6 + 1; } }
+    else if (kind == 1) { used = 2; made = (t6 & 7) + 4; }
+    else if (kind == 2) { used = 3; made = t6 + 1; }
+    return (used << 2) | (made << 16);
+}
+
+// One window of the successor table (one warp): every position of [w0, w0 + kIdxW) as if a tag started there, then
+// kIdxRounds rounds of pointer doubling between the warp's two buffers.  The last round is written to `final_s`: the
+// warp's own `tab` buffer (REMOTE false; the rounds are arranged to end there) or a table slot of the walker CTA of the
+// cluster (REMOTE true, a shared::cluster address).
+template <bool REMOTE>
+__device__ __forceinline__ void idx_build_window(uint32_t tab_s, uint32_t tmp_s, uint32_t lut_s, const uint8_t *gin,
+                                                 uint32_t w0, uint32_t in_end, uint32_t in_end16, uint32_t final_s,
+                                                 int lane) {
+    // (the asm accessors are volatile, i.e. executed in program order: loads are issued in batches of eight before
+    // their results are used, otherwise every position would pay the full LDS latency)
+    {
+        uint32_t word[kIdxW / 128];
+#pragma unroll
+        for (int k = 0; k < kIdxW / 128; k++) {
+            const uint32_t pos = w0 + 4u * ((uint32_t)lane + 32u * (uint32_t)k);
+            word[k] = pos < in_end16 ? __ldg(reinterpret_cast<const uint32_t *>(gin + pos)) : 0u;
+        }
+#pragma unroll
+        for (int h = 0; h < kIdxW / 128; h += 2) {
+            uint32_t e[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                e[q] = lds_u32(lut_s + (((word[h + (q >> 2)] >> (8 * (q & 3))) & 0xffu) << 2));
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const uint32_t wi = (uint32_t)lane + 32u * (uint32_t)(h + q);
+                const int32_t nv = (int32_t)(in_end - (w0 + 4u * wi));      // stream bytes in this word
+                if (nv < 4) {
+                    if (nv < 1) e[4 * q] = 0;
+                    if (nv < 2) e[4 * q + 1] = 0;
+                    if (nv < 3) e[4 * q + 2] = 0;
+                    e[4 * q + 3] = 0;
+                }
+                sts_v4((kIdxRounds & 1 ? tmp_s : tab_s) + 16u * wi, e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]);
+            }
+        }
+    }
+    __syncwarp();
+    // 2, 4, ... 2^kIdxRounds elements by pointer doubling (the low half of an entry is already a byte offset); the
+    // buffers alternate and the last round lands in `tab` (or in the remote slot)
+    uint32_t from_s = kIdxRounds & 1 ? tmp_s : tab_s, to_s = kIdxRounds & 1 ? tab_s : tmp_s;
+#pragma unroll 1
+    for (int r = 0; r < kIdxRounds; r++) {
+        const bool remote = REMOTE && r == kIdxRounds - 1;
+#pragma unroll 1
+        for (int k0 = 0; k0 < kIdxW / 32; k0 += 8) {
+            uint32_t e[8], f[8];
+            const uint32_t a0 = from_s + 4u * ((uint32_t)lane + 32u * (uint32_t)k0);
+#pragma unroll
+            for (int q = 0; q < 8; q++) e[q] = lds_u32(a0 + 128u * q);
+#pragma unroll
+            for (int q = 0; q < 8; q++) f[q] = lds_u32(a0 + 128u * q + (e[q] & 0xffffu));   // e == 0 re-reads itself
+            if (remote) {
+#pragma unroll
+                for (int q = 0; q < 8; q++) cluster_sts_u32(a0 - from_s + final_s + 128u * q, e[q] + f[q]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; q++) sts_u32(a0 - from_s + to_s + 128u * q, e[q] + f[q]);
+            }
+        }
+        __syncwarp();
+        const uint32_t t = from_s; from_s = to_s; to_s = t;
+    }
+}
+
+// The walker's state and its pass over one window: follows the chain through the window's table (`base` is the table's
+// shared-memory address minus 4 * the window's first position) and records fragment boundaries.  The whole warp runs
+// it on identical values (every load is a broadcast) and lane 0 writes the results: that way the elements around a
+// fragment boundary, which have to be taken one at a time from the stream itself, can be fetched by all lanes at once.
+struct IdxWalk {
+    uint32_t ip, op, next_b, k, flag;
+};
+__device__ __forceinline__ void idx_walk_window(IdxWalk &w, uint32_t base, uint32_t wend, uint32_t lut_s,
+                                                const uint8_t *gin, uint32_t in_begin, uint32_t in_end,
+                                                uint32_t *my_pos, uint32_t nfrag, int lane) {
+    uint32_t ip = w.ip, op = w.op, next_b = w.next_b, k = w.k, flag = w.flag;
+    for (;;) {
+        // the chain: one LDS + two adds per 2^kIdxRounds elements
+        uint32_t a = base + (ip << 2), e, adv;
+        // far from the next fragment boundary (an entry produces at most kIdxEntryOut bytes) the chain needs no
+        // test per hop: LDS -> mask -> add, four hops per round; a zero entry is a fixed point, so a stall
+        // inside the round shows in its last entry and neither `a` nor `op` moved past it
+        constexpr uint32_t kIdxEntryOut = 64u << kIdxRounds;
+        while (next_b - op > 4u * kIdxEntryOut) {
+            const uint32_t e1 = lds_u32(a);
+            a += e1 & 0xffffu;
+            const uint32_t e2 = lds_u32(a);
+            a += e2 & 0xffffu;
+            const uint32_t e3 = lds_u32(a);
+            a += e3 & 0xffffu;
+            const uint32_t e4 = lds_u32(a);
+            a += e4 & 0xffffu;
+            op += (e1 >> 16) + (e2 >> 16) + (e3 >> 16) + (e4 >> 16);
+            if ((e4 & 0xffffu) == 0) break;
+        }
+        for (;;) {
+            bool out = false;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                e = lds_u32(a);
+                adv = e & 0xffffu;
+                if (adv == 0 || op + (e >> 16) >= next_b) { out = true; break; }
+                a += adv;
+                op += e >> 16;
+            }
+            if (out) break;
+        }
+        ip = (a - base) >> 2;
+        if (adv == 0) {
+            if (ip >= wend) break;
+            // slow-path element: its length is in the stream, not in the tag
+            const uint32_t tag = gin[ip];
+            uint32_t used, made;
+            if ((tag & 3) == 3) { used = 5; made = (tag >> 2) + 1; }
+            else if ((tag & 3) == 0 && (tag >> 2) >= 60) {
+                const uint32_t nb = (tag >> 2) - 59;
+                uint32_t v = 0;
+                for (uint32_t i = 0; i < nb && ip + 1 + i < in_end; i++) v |= (uint32_t)gin[ip + 1 + i] << (8 * i);
+                made = v + 1;
+                used = 1 + nb + made;
+                if (made > in_end - ip || used > in_end - ip) { flag = 1; break; }
+            } else { flag = 1; break; }
+            if (op == next_b && k < nfrag) {
+                if (lane == 0) my_pos[k] = ip - in_begin;
+                k++;
+                next_b += kSnappyFragment;
+            } else if (op < next_b && made > next_b - op) { flag = 1; break; }
+            ip += used;
+            op += made;
+            if (ip >= wend) break;      // a long literal usually leaves the window (and several more)
+            continue;
+        }
+        const uint32_t op2 = op + (e >> 16);
+        if (op2 >= next_b) {
+            // a fragment boundary lies in (or right behind) these elements: take them one at a time.  Their tags come from
+            // the stream in HBM - read serially that was ~30 dependent loads of ~0.3 us per boundary, a quarter of the
+            // time of a 1 MiB page (r2w capture) - so the warp fetches 256 bytes at once (8 per lane) and the tags are
+            // picked out of the lanes' registers.
+            const uint32_t hop_end = ip + (adv >> 2);
+            uint32_t st0 = ip, st_lo = 0, st_hi = 0;
+            bool staged = false;
+            while (ip < hop_end) {
+                if (!staged || ip - st0 >= 256u) {
+                    st0 = ip;
+                    st_lo = st_hi = 0;
+                    const uint32_t q = st0 + 8u * (uint32_t)lane;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        if (q + i < in_end) st_lo |= (uint32_t)gin[q + i] << (8 * i);
+                        if (q + 4 + i < in_end) st_hi |= (uint32_t)gin[q + 4 + i] << (8 * i);
+                    }
+                    staged = true;
+                }
+                const uint32_t o = ip - st0;
+                const uint32_t wlo = __shfl_sync(0xffffffffu, st_lo, (int)(o >> 3));
+                const uint32_t whi = __shfl_sync(0xffffffffu, st_hi, (int)(o >> 3));
+                const uint32_t tag = (((o & 4u) ? whi : wlo) >> (8u * (o & 3u))) & 0xffu;
+                const uint32_t one = lds_u32(lut_s + (tag << 2));
+                const uint32_t made = one >> 16;
+                if (one == 0) { flag = 1; break; }   // cannot happen: the table came from the same bytes
+                if (op == next_b && k < nfrag) {
+                    if (lane == 0) my_pos[k] = ip - in_begin;
+                    k++;
+                    next_b += kSnappyFragment;
+                } else if (op < next_b && made > next_b - op) { flag = 1; break; }
+                ip += (one & 0xffffu) >> 2;
+                op += made;
+            }
+            if (flag) break;
+            continue;
+        }
+        ip += adv >> 2;
+        op = op2;
+    }
+    w.ip = ip; w.op = op; w.next_b = next_b; w.k = k; w.flag = flag;
+}
+// the stream's preamble: varint uncompressed length, which must match the page header
+__device__ __forceinline__ void idx_walk_preamble(IdxWalk &w, const uint8_t *gin, uint32_t in_end, uint32_t dst_n) {
+    uint64_t ulen = 0;
+    int shift = 0;
+    for (;;) {
+        if (w.ip >= in_end || shift > 35) { w.flag = 1; break; }
+        const uint8_t b = gin[w.ip++];
+        ulen |= (uint64_t)(b & 0x7f) << shift;
+        if (!(b & 0x80)) break;
+        shift += 7;
+    }
+    if (ulen != (uint64_t)dst_n) w.flag = 1;
+}
+
 __global__ void __launch_bounds__(kIdxThreads)
 k_snappy_index(const uint8_t *__restrict__ arena, const DevPage *__restrict__ pages,
                const int32_t *__restrict__ multi_list, int n_multi, uint32_t *__restrict__ frag_pos,
@@ -812,14 +1068,7 @@ k_snappy_index(const uint8_t *__restrict__ arena, const DevPage *__restrict__ pa
     const uint32_t in_end = in_begin + src_n;
     const uint32_t in_end16 = (in_end + 15) & ~15u;
 
-    for (int t = threadIdx.x; t < 256; t += kIdxThreads) {
-        const uint32_t kind = t & 3, t6 = t >> 2;
-        uint32_t used = 0, made = 0;
-        if (kind == 0) { if (t6 < 60) { used = t6 + 2; made = t6 + 1; } }
-        else if (kind == 1) { used = 2; made = (t6 & 7) + 4; }
-        else if (kind == 2) { used = 3; made = t6 + 1; }
-        lut[t] = (used << 2) | (made << 16);
-    }
+    for (int t = threadIdx.x; t < 256; t += kIdxThreads) lut[t] = idx_lut_entry((uint32_t)t);
     for (int t = threadIdx.x; t < kIdxBuilders * kIdxPad; t += kIdxThreads) {
         tab[t / kIdxPad][kIdxW + t % kIdxPad] = 0;
         tmp[t / kIdxPad][kIdxW + t % kIdxPad] = 0;
@@ -847,171 +1096,152 @@ k_snappy_index(const uint8_t *__restrict__ arena, const DevPage *__restrict__ pa
             if (use) idx_mbar_wait(my_empty, (use - 1) & 1u);      // the walker is done with the previous window of the slot
             const uint32_t w0 = j * kIdxW;
             const bool skip = __shfl_sync(0xffffffffu, (int)(give_up != 0 || w0 + kIdxW <= walker_ip), 0) != 0;
-            if (!skip) {
-                // (the asm accessors are volatile, i.e. executed in program order: loads are issued in batches of
-                // eight before their results are used, otherwise every position would pay the full LDS latency)
-                // one element: every position as if a tag started there
-                {
-                    uint32_t word[kIdxW / 128];
-#pragma unroll
-                    for (int k = 0; k < kIdxW / 128; k++) {
-                        const uint32_t pos = w0 + 4u * ((uint32_t)lane + 32u * (uint32_t)k);
-                        word[k] = pos < in_end16 ? __ldg(reinterpret_cast<const uint32_t *>(gin + pos)) : 0u;
-                    }
-#pragma unroll
-                    for (int h = 0; h < kIdxW / 128; h += 2) {
-                        uint32_t e[8];
-#pragma unroll
-                        for (int q = 0; q < 8; q++)
-                            e[q] = lds_u32(lut_s + (((word[h + (q >> 2)] >> (8 * (q & 3))) & 0xffu) << 2));
-#pragma unroll
-                        for (int q = 0; q < 2; q++) {
-                            const uint32_t wi = (uint32_t)lane + 32u * (uint32_t)(h + q);
-                            const int32_t nv = (int32_t)(in_end - (w0 + 4u * wi));      // stream bytes in this word
-                            if (nv < 4) {
-                                if (nv < 1) e[4 * q] = 0;
-                                if (nv < 2) e[4 * q + 1] = 0;
-                                if (nv < 3) e[4 * q + 2] = 0;
-                                e[4 * q + 3] = 0;
-                            }
-                            sts_v4((kIdxRounds & 1 ? tmp_s : tab_s) + 16u * wi, e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]);
-                        }
-                    }
-                }
-                __syncwarp();
-                // 2, 4, ... 2^kIdxRounds elements by pointer doubling (the low half of an entry is already a byte offset);
-                // the buffers alternate and the last round lands in `tab`
-                uint32_t from_s = kIdxRounds & 1 ? tmp_s : tab_s, to_s = kIdxRounds & 1 ? tab_s : tmp_s;
-#pragma unroll 1
-                for (int r = 0; r < kIdxRounds; r++) {
-#pragma unroll 1
-                    for (int k0 = 0; k0 < kIdxW / 32; k0 += 8) {
-                        uint32_t e[8], f[8];
-                        const uint32_t a0 = from_s + 4u * ((uint32_t)lane + 32u * (uint32_t)k0);
-#pragma unroll
-                        for (int q = 0; q < 8; q++) e[q] = lds_u32(a0 + 128u * q);
-#pragma unroll
-                        for (int q = 0; q < 8; q++) f[q] = lds_u32(a0 + 128u * q + (e[q] & 0xffffu));   // e == 0 re-reads itself
-#pragma unroll
-                        for (int q = 0; q < 8; q++) sts_u32(a0 - from_s + to_s + 128u * q, e[q] + f[q]);
-                    }
-                    __syncwarp();
-                    const uint32_t t = from_s; from_s = to_s; to_s = t;
-                }
-            }
+            if (!skip) idx_build_window<false>(tab_s, tmp_s, lut_s, gin, w0, in_end, in_end16, tab_s, lane);
             __syncwarp();
             if (lane == 0) idx_mbar_arrive(my_full);       // release: the table of window j is complete
         }
     } else {
         // ============================================ walker =====================================================
         const uint32_t lut_s = shared_addr(&lut[0]);
-        uint32_t ip = in_begin, op = 0, next_b = (uint32_t)kSnappyFragment, k = 1, flag = 0;
+        IdxWalk w{in_begin, 0u, (uint32_t)kSnappyFragment, 1u, 0u};
         uint32_t *const my_pos = frag_pos + pg.frag_first;
-        if (lane == 0) {
-            my_pos[0] = 0;
-            uint64_t ulen = 0;
-            int shift = 0;
-            for (;;) {
-                if (ip >= in_end || shift > 35) { flag = 1; break; }
-                const uint8_t b = gin[ip++];
-                ulen |= (uint64_t)(b & 0x7f) << shift;
-                if (!(b & 0x80)) break;
-                shift += 7;
-            }
-            if (ulen != (uint64_t)dst_n) flag = 1;
-            if (flag) give_up = 1;
-        }
+        if (lane == 0) my_pos[0] = 0;
+        idx_walk_preamble(w, gin, in_end, dst_n);
+        if (lane == 0 && w.flag) give_up = 1;
+        // (addresses once, slot and phase by counting: the per-window overhead of this loop is on the serial path)
+        const uint32_t tab_s0 = shared_addr(&tab[0][0]), full_s0 = (uint32_t)__cvta_generic_to_shared(&bar_full[0]);
+        const uint32_t empty_s0 = (uint32_t)__cvta_generic_to_shared(&bar_empty[0]);
+        uint32_t b = 0, phase = 0;
         for (uint32_t j = 0; j < nwin; j++) {
-            const int b = (int)(j % kIdxBuilders);
-            idx_mbar_wait((uint32_t)__cvta_generic_to_shared(&bar_full[b]), (j / kIdxBuilders) & 1u);
+            idx_mbar_wait(full_s0 + 8u * b, phase);
             const uint32_t wend = min((j + 1) * (uint32_t)kIdxW, in_end);
-            if (lane == 0 && !flag && ip < wend) {
-                const uint32_t base = shared_addr(&tab[b][0]) - ((j * (uint32_t)kIdxW) << 2);
-                for (;;) {
-                    // the chain: one LDS + two adds per 16 elements; forward exits only, one backward branch per 4 hops
-                    uint32_t a = base + (ip << 2), e, adv;
-                    // far from the next fragment boundary (an entry produces at most kIdxEntryOut bytes) the chain needs no
-                    // test per hop: LDS -> mask -> add, four hops per round; a zero entry is a fixed point, so a stall
-                    // inside the round shows in its last entry and neither `a` nor `op` moved past it
-                    constexpr uint32_t kIdxEntryOut = 64u << kIdxRounds;
-                    while (next_b - op > 4u * kIdxEntryOut) {
-                        const uint32_t e1 = lds_u32(a);
-                        a += e1 & 0xffffu;
-                        const uint32_t e2 = lds_u32(a);
-                        a += e2 & 0xffffu;
-                        const uint32_t e3 = lds_u32(a);
-                        a += e3 & 0xffffu;
-                        const uint32_t e4 = lds_u32(a);
-                        a += e4 & 0xffffu;
-                        op += (e1 >> 16) + (e2 >> 16) + (e3 >> 16) + (e4 >> 16);
-                        if ((e4 & 0xffffu) == 0) break;
-                    }
-                    for (;;) {
-                        bool out = false;
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            e = lds_u32(a);
-                            adv = e & 0xffffu;
-                            if (adv == 0 || op + (e >> 16) >= next_b) { out = true; break; }
-                            a += adv;
-                            op += e >> 16;
-                        }
-                        if (out) break;
-                    }
-                    ip = (a - base) >> 2;
-                    if (adv == 0) {
-                        if (ip >= wend) break;
-                        // slow-path element: its length is in the stream, not in the tag
-                        const uint32_t tag = gin[ip];
-                        uint32_t used, made;
-                        if ((tag & 3) == 3) { used = 5; made = (tag >> 2) + 1; }
-                        else if ((tag & 3) == 0 && (tag >> 2) >= 60) {
-                            const uint32_t nb = (tag >> 2) - 59;
-                            uint32_t v = 0;
-                            for (uint32_t i = 0; i < nb && ip + 1 + i < in_end; i++) v |= (uint32_t)gin[ip + 1 + i] << (8 * i);
-                            made = v + 1;
-                            used = 1 + nb + made;
-                            if (made > in_end - ip || used > in_end - ip) { flag = 1; break; }
-                        } else { flag = 1; break; }
-                        if (op == next_b && k < (uint32_t)pg.nfrag) { my_pos[k++] = ip - in_begin; next_b += kSnappyFragment; }
-                        else if (op < next_b && made > next_b - op) { flag = 1; break; }
-                        ip += used;
-                        op += made;
-                        if (ip >= wend) break;      // a long literal usually leaves the window (and several more)
-                        continue;
-                    }
-                    const uint32_t op2 = op + (e >> 16);
-                    if (op2 >= next_b) {
-                        // a fragment boundary lies in (or right behind) these elements: take them one at a time
-                        const uint32_t hop_end = ip + (adv >> 2);
-                        while (ip < hop_end) {
-                            const uint32_t one = lds_u32(lut_s + ((uint32_t)gin[ip] << 2));
-                            const uint32_t made = one >> 16;
-                            if (one == 0) { flag = 1; break; }   // cannot happen: the table came from the same bytes
-                            if (op == next_b && k < (uint32_t)pg.nfrag) { my_pos[k++] = ip - in_begin; next_b += kSnappyFragment; }
-                            else if (op < next_b && made > next_b - op) { flag = 1; break; }
-                            ip += (one & 0xffffu) >> 2;
-                            op += made;
-                        }
-                        if (flag) break;
-                        continue;
-                    }
-                    ip += adv >> 2;
-                    op = op2;
-                }
-                if (flag) give_up = 1;
+            if (!w.flag && w.ip < wend) {
+                idx_walk_window(w, tab_s0 + b * (uint32_t)sizeof(tab[0]) - ((j * (uint32_t)kIdxW) << 2), wend, lut_s, gin,
+                                in_begin, in_end, my_pos, (uint32_t)pg.nfrag, lane);
+                if (lane == 0 && w.flag) give_up = 1;
             }
-            if (lane == 0) walker_ip = ip;
+            if (lane == 0) walker_ip = w.ip;
             __syncwarp();
-            if (lane == 0 && j + kIdxBuilders < nwin)
-                idx_mbar_arrive((uint32_t)__cvta_generic_to_shared(&bar_empty[b]));
+            if (lane == 0 && j + kIdxBuilders < nwin) idx_mbar_arrive(empty_s0 + 8u * b);
+            if (++b == (uint32_t)kIdxBuilders) { b = 0; phase ^= 1u; }
         }
+        const uint32_t ip = w.ip, op = w.op, k = w.k;
+        uint32_t flag = w.flag;
         if (lane == 0) {
             if (!flag && (ip != in_end || op != dst_n || k != (uint32_t)pg.nfrag)) flag = 1;
             if (!flag) my_pos[pg.nfrag] = src_n;
             page_flag[pg.multi_slot] = flag;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K2a for BIG pages: the same index, one thread-block CLUSTER of four CTAs (four SMs) per page.
+//
+// In k_snappy_index the twelve builders and the walker share the shared-memory pipe of one SM: the doubling rounds keep it
+// ~90 % busy (the data-dependent second load of a round is a ~3.5-way bank conflict), so the walker's chain - five
+// dependent shared-memory loads per window - waits in the same queue and a 1 MiB page (950 windows; C2 has sixteen of
+// them, the int64 dictionary pages) takes 0.65 ms however many builders there are (r2t capture: 36 % of the builders'
+// samples are waits for the walker, the walker is never idle).  Here the walker has an SM to itself: CTA 0 of the cluster
+// holds one table slot per builder (36 x 4.25 KiB) and runs the walker warp; CTAs 1-3 run twelve builders each, which do
+// their doubling rounds in their own shared memory and write the LAST round straight into their slot in CTA 0 through
+// distributed shared memory (st.shared::cluster), then arrive on the slot's mbarrier in CTA 0
+// (mbarrier.arrive.release.cluster); the walker hands a slot back by arriving on the builder's own barrier in the
+// builder's CTA.  Pages below kIdxBigPage stay with the single-CTA kernel, which spends fewer SM-cycles per window.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kIdxCluster = 4;
+constexpr int kIdxSlots = (kIdxCluster - 1) * kIdxBuilders;
+constexpr size_t kIdxClusterSmemBytes = (size_t)kIdxSlots * (kIdxW + kIdxPad) * sizeof(uint32_t);
+static_assert(kIdxClusterSmemBytes >= kIdxSmemBytes, "builder CTAs use the front of the same allocation for tab/tmp");
+
+__global__ void __cluster_dims__(kIdxCluster, 1, 1) __launch_bounds__(kIdxThreads)
+k_snappy_index_cluster(const uint8_t *__restrict__ arena, const DevPage *__restrict__ pages,
+                       const int32_t *__restrict__ list, int n_list, uint32_t *__restrict__ frag_pos,
+                       uint32_t *__restrict__ page_flag) {
+    extern __shared__ __align__(16) uint8_t idx_smem[];
+    typedef uint32_t Table[kIdxW + kIdxPad];
+    Table *const slots = reinterpret_cast<Table *>(idx_smem);          // CTA 0: kIdxSlots final tables
+    Table *const tab = slots;                                          // CTAs 1..: the builders' two working buffers
+    Table *const tmp = slots + kIdxBuilders;
+    __shared__ __align__(8) uint64_t bar_full[kIdxSlots];              // used in CTA 0 (remote arrivals from the builders)
+    __shared__ __align__(8) uint64_t bar_empty[kIdxBuilders];          // used in CTAs 1.. (remote arrivals from the walker)
+    __shared__ uint32_t lut[256];
+    const uint32_t rank = cluster_ctarank();
+    const int li = (int)(blockIdx.x / kIdxCluster);                    // the grid is exactly n_list clusters
+    const int pi = list[min(li, n_list - 1)];
+    const DevPage pg = pages[pi];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    const uint8_t *src = arena + pg.src_off;
+    uint32_t src_n = (uint32_t)pg.comp_size;
+    uint32_t dst_n = (uint32_t)pg.uncomp_size;
+    if (pg.kind == PK_DATA_V2) {
+        const uint32_t lv = (uint32_t)(pg.def_bytes + pg.rep_bytes);
+        src += lv; src_n -= lv; dst_n -= lv;
+    }
+    const uint8_t *gin = src - ((uintptr_t)src & 15);
+    const uint32_t in_begin = (uint32_t)((uintptr_t)src & 15);
+    const uint32_t in_end = in_begin + src_n;
+    const uint32_t in_end16 = (in_end + 15) & ~15u;
+
+    for (int t = threadIdx.x; t < 256; t += kIdxThreads) lut[t] = idx_lut_entry((uint32_t)t);
+    // the zero entries behind every window (the builders never write them)
+    const int n_tables = rank == 0 ? kIdxSlots : 2 * kIdxBuilders;
+    for (int t = threadIdx.x; t < n_tables * kIdxPad; t += kIdxThreads) slots[t / kIdxPad][kIdxW + t % kIdxPad] = 0;
+    if (threadIdx.x == 0) {
+        // full: every lane of the builder arrives for its own stores (a release by one lane would not cover the others')
+        for (int b = 0; b < kIdxSlots; b++) idx_mbar_init((uint32_t)__cvta_generic_to_shared(&bar_full[b]), 32);
+        for (int b = 0; b < kIdxBuilders; b++) idx_mbar_init((uint32_t)__cvta_generic_to_shared(&bar_empty[b]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    cluster_sync_all();       // barriers and pads of every CTA are in place before anybody reaches across
+    const uint32_t nwin = (in_end + kIdxW - 1) / kIdxW;
+
+    if (rank != 0 && warp < kIdxBuilders) {
+        // ============================================ builders (CTAs 1..3) =======================================
+        const uint32_t g = (rank - 1u) * (uint32_t)kIdxBuilders + (uint32_t)warp;        // slot in CTA 0
+        const uint32_t tab_s = shared_addr(&tab[warp][0]), tmp_s = shared_addr(&tmp[warp][0]);
+        const uint32_t lut_s = shared_addr(&lut[0]);
+        const uint32_t slot_c = cluster_map(shared_addr(&slots[g][0]), 0);               // my slot, in CTA 0
+        const uint32_t full_c = cluster_map((uint32_t)__cvta_generic_to_shared(&bar_full[g]), 0);
+        const uint32_t my_empty = (uint32_t)__cvta_generic_to_shared(&bar_empty[warp]);
+        uint32_t use = 0;
+        for (uint32_t j = g; j < nwin; j += kIdxSlots, use++) {
+            if (use) cluster_mbar_wait(my_empty, (use - 1) & 1u);      // the walker is done with the slot's previous window
+            idx_build_window<true>(tab_s, tmp_s, lut_s, gin, j * kIdxW, in_end, in_end16, slot_c, lane);
+            cluster_mbar_arrive(full_c);                               // all 32 lanes, each releasing its own remote stores
+        }
+    } else if (rank == 0 && warp == kIdxBuilders) {
+        // ============================================ walker (CTA 0) =============================================
+        const uint32_t lut_s = shared_addr(&lut[0]);
+        IdxWalk w{in_begin, 0u, (uint32_t)kSnappyFragment, 1u, 0u};
+        uint32_t *const my_pos = frag_pos + pg.frag_first;
+        if (lane == 0) my_pos[0] = 0;
+        idx_walk_preamble(w, gin, in_end, dst_n);
+        const uint32_t slots_s0 = shared_addr(&slots[0][0]), full_s0 = (uint32_t)__cvta_generic_to_shared(&bar_full[0]);
+        const uint32_t empty_s0 = (uint32_t)__cvta_generic_to_shared(&bar_empty[0]);
+        uint32_t g = 0, gb = 0, grank = 1, phase = 0;      // slot, its builder's warp and CTA, phase of the slot's barrier
+        for (uint32_t j = 0; j < nwin; j++) {
+            cluster_mbar_poll(full_s0 + 8u * g, phase);
+            const uint32_t wend = min((j + 1) * (uint32_t)kIdxW, in_end);
+            if (!w.flag && w.ip < wend)
+                idx_walk_window(w, slots_s0 + g * (uint32_t)sizeof(Table) - ((j * (uint32_t)kIdxW) << 2), wend, lut_s, gin,
+                                in_begin, in_end, my_pos, (uint32_t)pg.nfrag, lane);
+            __syncwarp();
+            // hand the slot back to its builder (relaxed: the walk above has consumed every value it loaded from the slot,
+            // and a release here would put a GPU-scope membar on the walker's chain)
+            if (lane == 0 && j + kIdxSlots < nwin) cluster_mbar_arrive_relaxed(cluster_map(empty_s0 + 8u * gb, grank));
+            if (++gb == (uint32_t)kIdxBuilders) { gb = 0; grank++; }
+            if (++g == (uint32_t)kIdxSlots) { g = 0; gb = 0; grank = 1; phase ^= 1u; }
+        }
+        if (lane == 0) {
+            uint32_t flag = w.flag;
+            if (!flag && (w.ip != in_end || w.op != dst_n || w.k != (uint32_t)pg.nfrag)) flag = 1;
+            if (!flag) my_pos[pg.nfrag] = src_n;
+            page_flag[pg.multi_slot] = flag;
+        }
+    }
+    cluster_sync_all();       // nobody leaves while its shared memory may still be written or read by a peer
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1625,6 +1855,8 @@ cudaError_t configure_decode_kernels() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_snappy_index, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kIdxSmemBytes);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_snappy_index_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kIdxClusterSmemBytes);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_decode_pages, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeShared));
 }
 
@@ -1632,6 +1864,13 @@ cudaError_t launch_snappy_index(uint8_t *arena, const DevPage *pages, const int3
                                 uint32_t *frag_pos, uint32_t *page_flag, cudaStream_t s) {
     if (n_multi <= 0) return cudaSuccess;
     k_snappy_index<<<n_multi, kIdxThreads, kIdxSmemBytes, s>>>(arena, pages, multi_list, n_multi, frag_pos, page_flag);
+    return cudaGetLastError();
+}
+cudaError_t launch_snappy_index_cluster(uint8_t *arena, const DevPage *pages, const int32_t *list, int n_list,
+                                        uint32_t *frag_pos, uint32_t *page_flag, cudaStream_t s) {
+    if (n_list <= 0) return cudaSuccess;
+    k_snappy_index_cluster<<<n_list * kIdxCluster, kIdxThreads, kIdxClusterSmemBytes, s>>>(arena, pages, list, n_list,
+                                                                                           frag_pos, page_flag);
     return cudaGetLastError();
 }
 

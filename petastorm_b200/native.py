@@ -44,7 +44,7 @@ class PlanInfo(Structure):
                 ('payload_bytes', c_int64), ('uncompressed_bytes', c_int64), ('num_pages', c_int32),
                 ('num_columns', c_int32), ('num_compressed_pages', c_int32), ('num_index_pages', c_int32),
                 ('num_unwrapped_pages', c_int32), ('num_copy_tiles', c_int32), ('num_decode_pages', c_int32),
-                ('num_snappy_fragments', c_int32), ('num_host_indexed_pages', c_int32), ('reserved_', c_int32)]
+                ('num_snappy_fragments', c_int32), ('num_host_indexed_pages', c_int32), ('num_cluster_index_pages', c_int32)]
 
 
 class PlanColumn(Structure):

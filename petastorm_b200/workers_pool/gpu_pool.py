@@ -175,6 +175,18 @@ class GpuPool(object):
             resolve_ahead(self._resolvers)
 
     def _worker_loop(self):
+        prof_path = os.environ.get('PST_POOL_PROFILE')      # diagnostics: cProfile of the issuing thread, dumped on exit
+        if prof_path:
+            import cProfile
+            prof = cProfile.Profile()
+            try:
+                prof.runcall(self._worker_loop_body)
+            finally:
+                prof.dump_stats('{}.{}'.format(prof_path, threading.get_ident()))
+        else:
+            self._worker_loop_body()
+
+    def _worker_loop_body(self):
         if self._device is not None:
             import torch
             torch.cuda.set_device(self._device)

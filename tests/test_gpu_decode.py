@@ -160,6 +160,18 @@ def test_c2_shape(tmp_path):
     path = str(tmp_path / 'c2.parquet')
     pq.write_table(pa.table(cols), path, compression='snappy', row_group_size=n)
     _compare_flat(path)
+    # latency mode: the 1 MiB dictionary pages of the int64 columns are indexed by four-CTA clusters (k_snappy_index_cluster)
+    import os
+    from petastorm_b200 import native, rowgroup
+    f = rowgroup.open_file(path)
+    plan = native.Plan(f, 0, list(range(f.num_columns)))
+    assert plan.info.num_cluster_index_pages >= 16
+    assert plan.info.num_index_pages > plan.info.num_cluster_index_pages
+    os.environ['PST_IDX_CLUSTER'] = '1'
+    try:
+        _compare_flat(path)
+    finally:
+        del os.environ['PST_IDX_CLUSTER']
 
 
 def test_list_column_levels(tmp_path):
