@@ -1,7 +1,8 @@
 // sm_100a decode kernels for Parquet pages resident in HBM.
 //
-//   k_snappy_index   K2a compressed offset of every 64 KiB output boundary of a Snappy page (builder warps + walker)
-//   k_snappy_pages   K2  raw-Snappy decompress, one CTA (parser warp + executor warp) per 64 KiB fragment
+//   k_snappy_index   K2a compressed offset of every 64 KiB output boundary of a Snappy page (builder warps + walker);
+//                        k_snappy_index_cluster: the same on a four-CTA cluster per page (opt-in, big pages)
+//   k_snappy_pages   K2  raw-Snappy decompress, one CTA (parser, placement and copy warp) per 64 KiB fragment
 //   k_ba_dict_index  K4  BYTE_ARRAY dictionary entry index ({offset,len} per entry)
 //   k_decode_pages   K3/K4/K5/K6  levels (RLE/bit-packed hybrid) + PLAIN / dictionary values + validity,
 //                    one CTA (256 threads) per data page
@@ -29,20 +30,21 @@ namespace pst {
 //
 //   warp P (parser)     finds where the elements START -- the inherently serial part, every tag position depends on the
 //                       previous element.  Tag bytes come from a shared-memory staging window filled by cp.async
-//                       (LDGSTS); for every 1 KiB of input all 32 lanes build successor tables (element length for
+//                       (LDGSTS); for every 768 bytes of input all 32 lanes build successor tables (element length for
 //                       every byte position, then the lengths of the four elements that follow each position), so
 //                       the chain costs one LDS + one dp4a per FOUR elements.  Output: <= 8 hop records per batch.
 //   warp A (placement)  decodes one element per lane, assigns output positions with a warp scan, validates, and moves
 //                       literal bytes staging -> ring.
 //   warp B (copy)       resolves back-references ring -> ring in dependency rounds (a copy runs once every element in
-//                       front of its source range is complete) and writes the ring through to HBM in >= 4 KiB
+//                       front of its source range is complete) and writes the ring through to HBM in >= 2 KiB
 //                       pieces (positions are biased so that ring and HBM agree modulo 16: plain 16-byte copies).
 //
-// The ring holds the most recent 16 KiB of output in shared memory, so the many tiny copies of a match-heavy stream
+// The ring holds the most recent 8 KiB of output in shared memory, so the many tiny copies of a match-heavy stream
 // never pay a global store -> L2 -> global load round trip.  Neighbouring warps hand batches over by a rendezvous on
 // one named barrier per pair (double-buffered slots): P parses batch b+1 while A places batch b and B copies batch
 // b-1.  Literals >= 1 KiB bypass staging and ring (one vectorised global -> global copy by B).  A back-reference that
-// reaches outside the ring, or into a bypassed literal, is served from the output already written to HBM.
+// reaches outside the ring, or into a bypassed literal, is served from the output already written to HBM, every lane
+// fetching its own source.  23 KB of shared memory and 64 registers per thread: ten CTAs per SM.
 //
 // Why this shape: measured on B200 (profiles/r1_snappy_v2_ring.txt ... r1_final_three_stage.txt) a lone warp retires
 // ~1 dependent instruction per ~5.5 cycles and a taken branch costs ~15, so the cost of a stream is (instructions on
@@ -161,53 +163,13 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
-template <int K>
-__device__ __forceinline__ uint32_t lds_u8_off(uint32_t addr) {      // immediate offsets: no address arithmetic per byte
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1+%2];\n" : "=r"(v) : "r"(addr), "n"(K));
-    return v;
-}
-template <int K>
-__device__ __forceinline__ void sts_u8_off(uint32_t addr, uint32_t v) {
-    asm volatile("st.shared.u8 [%0+%2], %1;\n" ::"r"(addr), "r"(v), "n"(K) : "memory");
-}
 // `len` >= 1 bytes from position sp of one power-of-two shared-memory buffer to position d of another (or the same), in
-// stream order.  The decoder's time goes with the number of instructions its three warps execute per batch, and the
-// byte moves were a quarter of them (11 instructions per byte with masked addresses, r2final source profile): runs that
-// do not wrap - all but a few per fragment - use two running addresses and immediate offsets, 3 instructions per byte.
-// `grouped`: the source does not overlap the last four bytes written (literals; back-references with distance >= 4), so
-// four loads may be issued before their stores.
+// stream order (a back-reference with distance < length re-reads its own output).  A rolled loop with masked addresses:
+// the variants with running addresses, grouped loads or word-wise moves all measured slower on the 3-5 byte elements of
+// numeric columns (profiles/experiments/r2k_lean_byte_moves.cu.txt), and unrolling costs
+// instruction-cache footprint, which this kernel is sensitive to.
 __device__ __forceinline__ void smem_bytes(uint32_t src_s, uint32_t smask, uint32_t sp, uint32_t dst_s, uint32_t dmask,
-                                           uint32_t d, uint32_t len, bool grouped) {
-    const uint32_t so = sp & smask, dof = d & dmask;
-#ifdef PST_SNAPPY_NOGROUP
-    grouped = false;
-#endif
-#ifndef PST_SNAPPY_LEAN
-    if (false)
-#else
-    if (so + len <= smask + 1u && dof + len <= dmask + 1u)
-#endif
-    {
-        uint32_t sa = src_s + so, da = dst_s + dof;
-        uint32_t n4 = len >> 2;
-        if (grouped) {
-            for (; n4; n4--, sa += 4, da += 4) {
-                const uint32_t v0 = lds_u8_off<0>(sa), v1 = lds_u8_off<1>(sa), v2 = lds_u8_off<2>(sa), v3 = lds_u8_off<3>(sa);
-                sts_u8_off<0>(da, v0); sts_u8_off<1>(da, v1); sts_u8_off<2>(da, v2); sts_u8_off<3>(da, v3);
-            }
-        } else {
-            for (; n4; n4--, sa += 4, da += 4) {
-                sts_u8_off<0>(da, lds_u8_off<0>(sa)); sts_u8_off<1>(da, lds_u8_off<1>(sa));
-                sts_u8_off<2>(da, lds_u8_off<2>(sa)); sts_u8_off<3>(da, lds_u8_off<3>(sa));
-            }
-        }
-        const uint32_t r = len & 3u;
-        if (r > 0) sts_u8_off<0>(da, lds_u8_off<0>(sa));
-        if (r > 1) sts_u8_off<1>(da, lds_u8_off<1>(sa));
-        if (r > 2) sts_u8_off<2>(da, lds_u8_off<2>(sa));
-        return;
-    }
+                                           uint32_t d, uint32_t len) {
 #pragma unroll 1
     for (uint32_t i = 0; i < len; i++) sts_u8(dst_s + ((d + i) & dmask), lds_u8(src_s + ((sp + i) & smask)));
 }
@@ -397,7 +359,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
             const uint32_t batch_start = ip;
             // ---- successor tables.  Finding where the elements START is the only serial part of Snappy: the position
             // of a tag depends on the element before it.  Instead of decoding tag after tag on that chain (~130 cycles
-            // per element for a lone lane), all 32 lanes first compute, for EVERY byte position of a 1 KiB window, how
+            // per element for a lone lane), all 32 lanes first compute, for EVERY byte position of a kTabW-byte window, how
             // long an element starting there would be (step_tab, via a 256-entry lookup of the tag byte) and from that
             // the lengths of the four consecutive elements that follow each position (quad_tab).  The chain is then
             // one shared-memory load + one dp4a per FOUR elements.  Positions that start a slow-path element, lie
@@ -604,7 +566,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
             if (!failed) {
                 // ---- literals: staging -> ring.  Short ones per lane, longer ones by the whole warp.
                 const bool is_lit = have && kind == 0;
-                if (is_lit && len <= 16) smem_bytes(stage_s, kStageMask, a, ring_s, kRingMask, d, len, true);
+                if (is_lit && len <= 16) smem_bytes(stage_s, kStageMask, a, ring_s, kRingMask, d, len);
                 uint32_t longs = __ballot_sync(0xffffffffu, is_lit && len > 16);
                 while (longs) {
                     const int l = __ffs(longs) - 1;
@@ -667,7 +629,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                 const bool in_ring = sp >= valid_from && dst_end - sp <= (uint32_t)kRing - kMaxBatchOut;
                 // the common case first: a source that ends in front of the batch depends on nothing in it
                 const bool early = is_copy && in_ring && src_end <= dst_begin;
-                if (early) smem_bytes(ring_s, kRingMask, d - a, ring_s, kRingMask, d, len, a >= 4u);
+                if (early) smem_bytes(ring_s, kRingMask, d - a, ring_s, kRingMask, d, len);
                 // a source outside the ring that this warp has already written to HBM depends on nothing either: every lane
                 // fetches its own.  (5 % of the C2 back-references.  The first version handled them one lane at a time in
                 // the dependency rounds with a flush in front - 3.8 % of the kernel's instructions and most of this warp's
@@ -708,7 +670,7 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
                         }
                     }
                     // sequential per lane: an overlapping copy (offset < length) re-reads its own bytes
-                    if (ready && in_ring) smem_bytes(ring_s, kRingMask, d - a, ring_s, kRingMask, d, len, a >= 4u);
+                    if (ready && in_ring) smem_bytes(ring_s, kRingMask, d - a, ring_s, kRingMask, d, len);
                     pending &= ~__ballot_sync(0xffffffffu, ready);
                     __syncwarp();
                 }
@@ -741,16 +703,18 @@ k_snappy_pages(uint8_t *__restrict__ arena, const DevPage *__restrict__ pages, c
 // fragments of all pages in parallel.  A page whose elements straddle a 64 KiB boundary, or whose stream is damaged,
 // gets its flag raised and is decoded as one stream by the serial fallback launch (which also reports the error).
 //
-// The walk is the serial part, so it is made as short as possible: four builder warps compute, for every byte position
-// of a 1 KiB input window, {bytes consumed, bytes produced} by the NEXT 16 ELEMENTS starting there (lookup of the tag
-// byte, then four rounds of pointer doubling T2[p] = T[p] + T[p + consumed(T[p])] in shared memory).  The walker lane
-// then needs one shared-memory load and two adds per 16 elements.  Positions holding a slow-path tag, behind the window
+// The walk is the serial part, so it is made as short as possible: twelve builder warps compute, for every byte position
+// of a 1 KiB input window, {bytes consumed, bytes produced} by the NEXT 64 ELEMENTS starting there (lookup of the tag
+// byte, then six rounds of pointer doubling T2[p] = T[p] + T[p + consumed(T[p])] in shared memory).  The walker warp
+// then needs one shared-memory load and two adds per 64 elements.  Positions holding a slow-path tag, behind the window
 // or behind the stream have {0, 0}, which stalls the chain there.
 // ---------------------------------------------------------------------------------------------------------------
-// Builders per CTA.  A builder warp needs ~6.4k cycles per 1 KiB window, the walker ~0.6k: with four builders (the first
-// version, named barriers) a 1 MiB page took 0.84 ms and the sixteen dictionary pages of the C2 int64 columns set the
-// latency of the whole launch; twelve builders make the walker the limit.  The hand-over uses mbarriers in shared memory
-// (one full / one empty barrier per builder): named barriers are limited to 16 per CTA.
+// What bounds it (r2t/r2w captures): the doubling rounds keep the SM's shared-memory pipe ~90 % busy (their second load
+// is data dependent: ~3.5-way bank conflicts), the walker executes ~140 dependent instructions per window, and both
+// come to ~1.3 k cycles per window - a 1 MiB page (950 windows; the sixteen dictionary pages of the C2 int64 columns)
+// takes 0.65 ms whether there are four builders (round 1: 0.84 ms with named barriers and 4 rounds) or twelve, 5 rounds
+// or 6.  Pages are launched longest first so that these do not start in the second wave.  The hand-over uses mbarriers
+// in shared memory (one full / one empty barrier per builder): named barriers are limited to 16 per CTA.
 constexpr int kIdxBuilders = 12;
 constexpr int kIdxThreads = 32 * (kIdxBuilders + 1);
 constexpr int kIdxW = 1024;

@@ -176,15 +176,20 @@ class GpuPool(object):
 
     def _worker_loop(self):
         prof_path = os.environ.get('PST_POOL_PROFILE')      # diagnostics: cProfile of the issuing thread, dumped on exit
+        prof = None
         if prof_path:
             import cProfile
             prof = cProfile.Profile()
             try:
-                prof.runcall(self._worker_loop_body)
-            finally:
-                prof.dump_stats('{}.{}'.format(prof_path, threading.get_ident()))
-        else:
+                prof.enable()
+            except ValueError:      # Python >= 3.12: one profiler per process (e.g. the consumer thread is being profiled)
+                prof = None
+        try:
             self._worker_loop_body()
+        finally:
+            if prof is not None:
+                prof.disable()
+                prof.dump_stats('{}.{}'.format(prof_path, threading.get_ident()))
 
     def _worker_loop_body(self):
         if self._device is not None:
