@@ -1368,7 +1368,7 @@ __device__ void hybrid_scan_warp(HybridCursor &c, RunTable &t, uint32_t want, in
         if (remaining == 0) {
             uint32_t h0, hlen0;
             if (!hybrid_header(p, end, h0, hlen0)) { error = 1; break; }
-            const uint32_t count0 = (h0 >> 1) * 8u;
+            const uint32_t count0 = min(h0 >> 1, 1u << 27) * 8u;      // (clamped: a damaged header must not wrap the arithmetic)
             if ((h0 & 1u) && count0 != 0) {
                 // ---- a sequence of identical bit-packed runs
                 const uint64_t stride = (uint64_t)hlen0 + (uint64_t)(h0 >> 1) * (uint64_t)bw;
