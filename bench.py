@@ -284,6 +284,9 @@ class Workload(object):
 
     @staticmethod
     def batch_rows(batch):
+        windows = getattr(batch, 'windows', None)      # NGram batch of the device loaders: {field: tensor[batch, L, ...]}
+        if windows is not None:
+            return int(next(iter(windows.values())).shape[0])
         first = batch[next(iter(batch))]
         if isinstance(first, dict):
             first = first[next(iter(first))]

@@ -18,8 +18,16 @@ _NORM_DTYPE = {torch.uint8: 0, torch.float16: 1, torch.float32: 2, torch.int32: 
 LAUNCH_CALLS = [0]
 
 
-def _stream():
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+
+
+def _stream(device_index=None):
+    """Handle of the current torch stream (of ``device_index`` when the caller knows it: the raw lookup costs a fraction
+    of a microsecond, ``torch.cuda.current_stream()`` ~15 - this runs once per kernel launch, and the per-batch calls of
+    the loaders are host-bound)."""
     LAUNCH_CALLS[0] += 1
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device() if device_index is None else device_index)
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -30,13 +38,16 @@ def _status(device):
 def gather_rows(src, index):
     """out[i] = src[index[i]] along dim 0 (K13; ``table.take`` / ``DataFrame.sample`` of the reference workers)."""
     assert src.is_cuda and src.is_contiguous()
-    index = index.to(device=src.device, dtype=torch.int64).contiguous()
+    if index.dtype != torch.int64 or index.device != src.device or not index.is_contiguous():
+        index = index.to(device=src.device, dtype=torch.int64).contiguous()
     n = index.numel()
-    out = torch.empty((n,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    inner = src.shape[1:]
+    out = torch.empty((n,) + tuple(inner), dtype=src.dtype, device=src.device)
     if n == 0:
         return out
-    row_bytes = src.element_size() * int(np.prod(src.shape[1:], dtype=np.int64)) if src.dim() > 1 else src.element_size()
-    check(lib.pst_gather_rows(src.data_ptr(), index.data_ptr(), n, row_bytes, out.data_ptr(), _stream()), 'gather_rows')
+    row_bytes = src.element_size() * math.prod(inner)
+    check(lib.pst_gather_rows(src.data_ptr(), index.data_ptr(), n, row_bytes, out.data_ptr(), _stream(src.device.index)),
+          'gather_rows')
     return out
 
 

@@ -349,15 +349,37 @@ class _RowPacker(object):
         return out
 
     def unpack(self, batch):
+        """Typed views of the packed batch, one ``as_strided`` per field over one reinterpretation of the buffer per dtype
+        (this runs once per batch on the consumer's thread; slicing + ``view`` + ``reshape`` per field was 72 us of a
+        170 us batch of C5 windows)."""
         res = {}
         rest = batch
         if self.small:
             packed, rest = batch[0], batch[1:]
             n = packed.shape[0]
-            for k, off, nb, dtype, shape in self.small:
-                res[k] = packed[:, off:off + nb].view(dtype).reshape((n,) + shape)
+            typed = {}
+            for k, off, nb, dtype, shape, item, strides in self._views():
+                base = typed.get(dtype)
+                if base is None:
+                    base = typed[dtype] = packed.view(dtype)
+                res[k] = torch.as_strided(base, (n,) + shape, (self.row_bytes // item,) + strides,
+                                          base.storage_offset() + off // item)
         res.update(zip(self.big, rest))
         return {k: res[k] for k in self.keys}
+
+    def _views(self):
+        views = getattr(self, '_view_plan', None)
+        if views is None:
+            views = []
+            for k, off, nb, dtype, shape in self.small:
+                item = torch.empty(0, dtype=dtype).element_size()
+                strides, acc = [], 1
+                for d in reversed(shape):
+                    strides.append(acc)
+                    acc *= d
+                views.append((k, off, nb, dtype, shape, item, tuple(reversed(strides))))
+            self._view_plan = views
+        return views
 
 
 def _iter_device_batches(groups, batch_size, shuffling_queue_capacity, transform_fn):
