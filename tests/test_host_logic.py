@@ -798,3 +798,24 @@ def test_planner_indexes_blob_pages_on_the_host(tmp_path):
                    compression='snappy', use_dictionary=False, data_page_size=1 << 20)
     info = native.Plan(native.ParquetFile(path), 0, [0]).info
     assert info.num_index_pages >= 2 and info.num_host_indexed_pages == 0
+
+
+def test_planner_counts_the_pages_of_the_cluster_index(tmp_path):
+    """Pages of >= 256 KiB stored bytes among those the device has to index (the 1 MiB dictionary pages pyarrow writes for
+    int64 columns of more than 131,072 distinct values) are the ones the opt-in four-CTA cluster variant of the index
+    kernel takes (PST_IDX_CLUSTER=1); the float32 dictionary pages of random values are literal-only Snappy and never
+    reach the device index at all."""
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    from petastorm_b200 import native
+    n = 300000
+    rng = np.random.default_rng(7)
+    path = str(tmp_path / 'c2like.parquet')
+    pq.write_table(pa.table({'f0': rng.standard_normal(n).astype(np.float32), 'f1': rng.standard_normal(n).astype(np.float32),
+                             'i0': rng.integers(0, 2 ** 40, n, dtype=np.int64),
+                             'i1': rng.integers(0, 2 ** 40, n, dtype=np.int64)}), path, compression='snappy',
+                   row_group_size=n)
+    info = native.Plan(native.ParquetFile(path), 0, [0, 1, 2, 3]).info
+    assert info.num_cluster_index_pages == 2                     # one dictionary page per int64 column
+    assert info.num_index_pages > info.num_cluster_index_pages   # their data pages stay with the single-CTA kernel
+    assert info.num_unwrapped_pages >= 2                         # the float columns never see the Snappy kernels
