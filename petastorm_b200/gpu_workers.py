@@ -1000,9 +1000,9 @@ class GpuPyDictWorker(_GpuWorkerBase):
             payload = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
             if data_off + payload == len(member):
                 dense_blobs, st = device_ops.zip_inflate_batch(col, len(member), live_dev)
-                if int(st[0].item()) == 0:
+                if int(device_ops.to_host(st)[0]) == 0:
                     out, status = device_ops.npy_batch(dense_blobs, data_off, payload, _TORCH_OF_NUMPY[dtype], shape)
-                    if int(status[0].item()) == 0:
+                    if int(device_ops.to_host(status)[0]) == 0:
                         return out
         blobs = rowgroup.gather_blobs_to_host(col, live)
         return [codec.decode(field, b) for b in blobs]
@@ -1011,7 +1011,7 @@ class GpuPyDictWorker(_GpuWorkerBase):
         if len(live) == 0:
             return []
         device = col.arena.device
-        heads = device_ops.blob_prefix(col, 256).cpu().numpy()   # one small D2H for all headers of the row-group
+        heads = device_ops.to_host(device_ops.blob_prefix(col, 256)).numpy()   # one small D2H for all headers of the row-group
         groups = {}
         for pos, r in enumerate(live):
             b = heads[r].tobytes()
@@ -1022,7 +1022,7 @@ class GpuPyDictWorker(_GpuWorkerBase):
             if dtype in _TORCH_OF_NUMPY and not fortran and dtype.byteorder in ('=', '<', '|'):
                 payload = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
                 out, status = device_ops.npy_batch(col, data_off, payload, _TORCH_OF_NUMPY[dtype], shape, live_dev)
-                if int(status[0].item()) == 0:
+                if int(device_ops.to_host(status)[0]) == 0:
                     return out
         # ragged shapes / string dtypes / fortran order: decode each group; string arrays have no tensor form
         result = [None] * len(live)
@@ -1039,7 +1039,7 @@ class GpuPyDictWorker(_GpuWorkerBase):
                 payload = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
                 idx = torch.from_numpy(np.ascontiguousarray(rows.astype(np.int64))).to(device)
                 out, status = device_ops.npy_batch(col, data_off, payload, _TORCH_OF_NUMPY[dtype], shape, idx)
-                if int(status[0].item()) == 0:
+                if int(device_ops.to_host(status)[0]) == 0:
                     for k, p in enumerate(positions):
                         result[p] = out[k]
                     continue
@@ -1057,13 +1057,13 @@ class GpuPyDictWorker(_GpuWorkerBase):
         if shape and None not in shape and len(shape) in (2, 3) and np_dtype in (np.dtype('uint8'), np.dtype('uint16')):
             ch = shape[2] if len(shape) == 3 else 1
             out, status = device_ops.png_batch(col, shape[0], shape[1], ch, _TORCH_OF_NUMPY[np_dtype], live_dev)
-            st = status.cpu().tolist()
+            st = device_ops.to_host(status).tolist()
             if st[0] == 0:
                 return out
             if st[0] == 7:
                 raise ValueError('corrupt PNG stream in row {} of the row-group'.format(st[1]))
             # geometry differs from the schema (or unsupported variant): take the per-header path below
-        heads = device_ops.blob_prefix(col, 33).cpu().numpy()
+        heads = device_ops.to_host(device_ops.blob_prefix(col, 33)).numpy()
         groups = {}
         for pos, r in enumerate(live):
             h = heads[r]
@@ -1076,7 +1076,7 @@ class GpuPyDictWorker(_GpuWorkerBase):
                 raise ValueError('Unexpected image dimensions. Supported dimensions are (H, W) or (H, W, 3).')
             idx = torch.from_numpy(np.ascontiguousarray(live[positions].astype(np.int64))).to(device)
             out, status = device_ops.png_batch(col, hgt, w, ch, torch.uint8 if depth == 8 else torch.uint16, idx)
-            st = status.cpu().tolist()
+            st = device_ops.to_host(status).tolist()
             if st[0] != 0:
                 raise ValueError('PNG decode failed (code {}) in row {}'.format(st[0], st[1]))
             for k, p in enumerate(positions):
@@ -1093,10 +1093,10 @@ class GpuPyDictWorker(_GpuWorkerBase):
         live = np.asarray(live)
         if device_ops.jpeg_device_backend() < 0 or _FORCE_HOST_JPEG[0]:
             return self._decode_jpeg_host_staged(col, field, live)
-        offs = col.offs.cpu().numpy()[live]
-        lens = col.lens.cpu().numpy()[live]
+        offs = device_ops.to_host(col.offs).numpy()[live]
+        lens = device_ops.to_host(col.lens).numpy()[live]
         # geometry of every stream from its SOF marker (nvJPEG writes what the stream says: the output buffers must fit)
-        hw = _jpeg_sizes(device_ops.blob_prefix(col, 1024).cpu().numpy()[live])
+        hw = _jpeg_sizes(device_ops.to_host(device_ops.blob_prefix(col, 1024)).numpy()[live])
         shape = field.shape
         if shape and None not in shape and len(shape) == 3 and shape[2] == 3:
             bad = np.nonzero((hw[:, 0] != shape[0]) | (hw[:, 1] != shape[1]))[0]
