@@ -819,3 +819,31 @@ def test_planner_counts_the_pages_of_the_cluster_index(tmp_path):
     assert info.num_cluster_index_pages == 2                     # one dictionary page per int64 column
     assert info.num_index_pages > info.num_cluster_index_pages   # their data pages stay with the single-CTA kernel
     assert info.num_unwrapped_pages >= 2                         # the float columns never see the Snappy kernels
+
+
+def test_row_packer_views_are_the_columns_again():
+    """The device loaders pack the narrow columns of a row-group into one uint8 [n, R] buffer and hand batches out as
+    typed strided views of it (one as_strided per field): values, dtypes and shapes must survive, also for a batch that
+    is a slice of the buffer (non-zero storage offset) and for the wide columns that stay separate."""
+    import torch
+    from petastorm_b200.pytorch import _RowPacker
+    n = 37
+    g = torch.Generator().manual_seed(3)
+    cols = {'ts': torch.arange(n * 16, dtype=torch.int64).reshape(n, 16),
+            'a': torch.randn(n, 16, generator=g), 'b': torch.randn(n, 16, 2, generator=g),
+            'c': torch.randint(0, 100, (n,), dtype=torch.int32, generator=g),
+            'img': torch.randn(n, 3, 64, 64, generator=g),
+            'u': torch.randint(0, 255, (n, 5), dtype=torch.uint8, generator=g)}
+    packer = _RowPacker(cols)
+    assert [v[0] for v in packer.small] == ['ts', 'a', 'b', 'c', 'u'] and packer.big == ['img']
+    assert packer.row_bytes % 16 == 0
+    packed = packer.pack(cols)
+    assert len(packed) == 2 and packed[0].dtype == torch.uint8 and packed[0].shape == (n, packer.row_bytes)
+    for batch, expect in ((packed, cols), ([t[5:20] for t in packed], {k: v[5:20] for k, v in cols.items()})):
+        out = packer.unpack(batch)
+        assert list(out) == list(cols)
+        for k in cols:
+            assert out[k].dtype == cols[k].dtype and out[k].shape == expect[k].shape
+            assert torch.equal(out[k], expect[k]), k
+    # a single narrow column is not worth a packed buffer
+    assert _RowPacker({'x': cols['a'], 'img': cols['img']}).small == []
